@@ -1,0 +1,28 @@
+#!/usr/bin/env bash
+# Builds agents_b200/lib/libb200rl.so for sm_100a (nvcc cross-compiles without a GPU).
+set -euo pipefail
+here="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+out="$here/../lib"
+mkdir -p "$out" "$here/obj"
+NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
+FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
+       --expt-relaxed-constexpr -Xptxas -v)
+pids=()
+for f in "$here"/*.cu; do
+  o="$here/obj/$(basename "${f%.cu}").o"
+  if [[ ! -f "$o" || "$f" -nt "$o" || "$here/common.cuh" -nt "$o" || "$here/../../include/b200rl.h" -nt "$o" ]]; then
+    "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 &
+    pids+=($!)
+  fi
+done
+rc=0
+for p in "${pids[@]:-}"; do
+  [[ -z "$p" ]] && continue
+  wait "$p" || rc=1
+done
+if [[ $rc -ne 0 ]]; then
+  cat "$here"/obj/*.log | grep -E "error|Error" -A3 | head -80
+  exit 1
+fi
+"$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$out/libb200rl.so" "$here"/obj/*.o -lcudart_static -ldl -lrt -lpthread
+echo "built $out/libb200rl.so"

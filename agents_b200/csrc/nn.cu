@@ -1,0 +1,531 @@
+// Dense / Conv2D forward + backward in true fp32 (kernel family iii, network part).
+//
+// The reference runs these through Keras -> TensorFlow CPU kernels (Eigen fp32):
+//   networks/encoding_network.py:224-312 (conv + dense stack), q_network.py:126-135 (Q head),
+//   examples/dqn/mnih15/dqn_train_eval_atari.py:104-110 (the Atari net incl. cast+/255).
+// North-star parity is 1e-5 relative on the loss, which BF16/TF32 MMA cannot hold over a
+// 3136-wide reduction (SURVEY.md §7 "hard parts"), so this file is a register-tiled fp32 FFMA
+// GEMM with pluggable operand views:
+//   ARow  A(m,k)=X[m*ld+k]              dense forward, dX = dZ @ W^T
+//   ACol  A(m,k)=X[k*ld+m]              dW = X^T @ dZ
+//   AConv A(m,k)=im2col(X)(m,k)         implicit-GEMM conv forward (u8 or f32 input, fused
+//                                       cast * scale of the reference's preprocessing layer)
+//   AConvT A(m,k)=im2col(X)(k,m)        conv filter gradient
+//   BRow  B(k,n)=W[k*ld+n]   BCol  B(k,n)=W[n*ld+k]
+// Small output grids (fc layers, filter gradients) use deterministic split-K: partial tiles
+// go to the caller's workspace and a second kernel reduces them in fixed order and applies
+// bias + activation, so results are run-to-run bit-stable.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace b200rl {
+
+struct FastDiv {
+  uint32_t d, mul, shr;
+  __host__ FastDiv() : d(1), mul(0), shr(0) {}
+  __host__ explicit FastDiv(uint32_t div) : d(div) {
+    // round-up magic number method, valid for n < 2^31
+    if (div == 1) { mul = 0; shr = 0; return; }
+    uint32_t l = 0;
+    while ((1u << l) < div) ++l;
+    uint64_t m = ((1ull << 32) * ((1ull << l) - div)) / div + 1;
+    mul = (uint32_t)m;
+    shr = l;
+  }
+  __device__ __forceinline__ uint32_t div(uint32_t n) const {
+    if (d == 1) return n;
+    uint32_t t = __umulhi(mul, n);
+    return (t + ((n - t) >> 1)) >> (shr - 1);
+  }
+  __device__ __forceinline__ void divmod(uint32_t n, uint32_t& q, uint32_t& r) const {
+    q = div(n);
+    r = n - q * d;
+  }
+};
+
+struct ARow {
+  const float* p;
+  int64_t ld;
+  static constexpr bool kKContig = true;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[m * ld + k]; }
+};
+struct ACol {
+  const float* p;
+  int64_t ld;
+  static constexpr bool kKContig = false;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
+};
+struct BRow {
+  const float* p;
+  int64_t ld;
+  static constexpr bool kNContig = true;
+  __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
+};
+struct BCol {
+  const float* p;
+  int64_t ld;
+  static constexpr bool kNContig = false;
+  __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[n * ld + k]; }
+};
+
+struct ConvGeom {
+  int H, W, C, KH, KW, F, stride, OH, OW;
+  FastDiv d_ohow, d_ow, d_kwc;
+  int64_t in_row;   // W*C
+  int64_t in_img;   // H*W*C
+};
+
+template <typename T>
+__device__ __forceinline__ float cvt_in(T v, float scale);
+template <>
+__device__ __forceinline__ float cvt_in<float>(float v, float) { return v; }
+template <>
+__device__ __forceinline__ float cvt_in<uint8_t>(uint8_t v, float scale) {
+  // tf.cast(obs, f32) / 255 is restated as a division to stay bit-identical to the oracle.
+  return __fdiv_rn((float)v, scale);
+}
+
+// im2col view: pos = (n, oy, ox), patch = (ky, kx, c) with c fastest (Keras HWIO order).
+template <typename T>
+struct ConvView {
+  const T* x;
+  ConvGeom g;
+  float scale;
+  __device__ __forceinline__ int64_t pos_offset(uint32_t pos) const {
+    uint32_t n, r, oy, ox;
+    g.d_ohow.divmod(pos, n, r);
+    g.d_ow.divmod(r, oy, ox);
+    return (int64_t)n * g.in_img + (int64_t)(oy * g.stride) * g.in_row +
+           (int64_t)(ox * g.stride) * g.C;
+  }
+  __device__ __forceinline__ int64_t patch_offset(uint32_t kidx) const {
+    uint32_t ky, r;
+    g.d_kwc.divmod(kidx, ky, r);
+    return (int64_t)ky * g.in_row + r;
+  }
+  __device__ __forceinline__ float load(int64_t off) const { return cvt_in<T>(x[off], scale); }
+};
+template <typename T>
+struct AConv {
+  ConvView<T> v;
+  static constexpr bool kKContig = true;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const {
+    return v.load(v.pos_offset((uint32_t)m) + v.patch_offset((uint32_t)k));
+  }
+};
+template <typename T>
+struct AConvT {
+  ConvView<T> v;
+  static constexpr bool kKContig = false;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const {
+    return v.load(v.pos_offset((uint32_t)k) + v.patch_offset((uint32_t)m));
+  }
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == B200RL_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == B200RL_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+constexpr int BK = 16;
+
+// C[M,N] (+)= act(A @ B + bias)   or   ws[split] = partial(A @ B) when splits > 1.
+template <int BM, int BN, int TM, int TN, class AL, class BL>
+__global__ void __launch_bounds__(256) sgemm_kernel(const AL a, const BL b, float* __restrict__ C,
+                                                    const float* __restrict__ bias, int64_t M,
+                                                    int64_t N, int64_t K, int act, int beta,
+                                                    int splits, int64_t k_per_split,
+                                                    float* __restrict__ ws) {
+  static_assert((BM / TM) * (BN / TN) == 256, "thread grid must be 256");
+  constexpr int TX = BN / TN;
+  constexpr int GM = TM >= 4 ? 4 : TM, GN = TN >= 4 ? 4 : TN;  // contiguous group widths
+  constexpr int NGM = TM / GM, NGN = TN / GN;
+  constexpr int APT = BM * BK / 256, BPT = BN * BK / 256;  // elements per thread per tile
+  __shared__ __align__(16) float As[2][BK][BM + 4];
+  __shared__ __align__(16) float Bs[2][BK][BN + 4];
+
+  const int tid = threadIdx.x;
+  const int tx = tid % TX, ty = tid / TX;
+  const int64_t m0 = (int64_t)blockIdx.y * BM, n0 = (int64_t)blockIdx.x * BN;
+  const int split = blockIdx.z;
+  const int64_t kb = (int64_t)split * k_per_split;
+  const int64_t ke = (kb + k_per_split < K) ? kb + k_per_split : K;
+
+  // tile-load coordinates
+  int a_m[APT], a_k[APT], b_n[BPT], b_k[BPT];
+#pragma unroll
+  for (int i = 0; i < APT; ++i) {
+    if (AL::kKContig) { a_k[i] = tid % BK; a_m[i] = tid / BK + i * (256 / BK); }
+    else { a_m[i] = tid % BM; a_k[i] = tid / BM + i * (256 / BM); }
+  }
+#pragma unroll
+  for (int i = 0; i < BPT; ++i) {
+    if (BL::kNContig) { b_n[i] = tid % BN; b_k[i] = tid / BN + i * (256 / BN); }
+    else { b_k[i] = tid % BK; b_n[i] = tid / BK + i * (256 / BK); }
+  }
+
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+
+  float ra[APT], rb[BPT];
+  auto load_tile = [&](int64_t k0) {
+#pragma unroll
+    for (int i = 0; i < APT; ++i) {
+      const int64_t m = m0 + a_m[i], k = k0 + a_k[i];
+      ra[i] = (m < M && k < ke) ? a.at(m, k) : 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) {
+      const int64_t n = n0 + b_n[i], k = k0 + b_k[i];
+      rb[i] = (n < N && k < ke) ? b.at(k, n) : 0.f;
+    }
+  };
+  auto store_tile = [&](int buf) {
+#pragma unroll
+    for (int i = 0; i < APT; ++i) As[buf][a_k[i]][a_m[i]] = ra[i];
+#pragma unroll
+    for (int i = 0; i < BPT; ++i) Bs[buf][b_k[i]][b_n[i]] = rb[i];
+  };
+
+  int buf = 0;
+  if (kb < ke) {
+    load_tile(kb);
+    store_tile(0);
+  }
+  __syncthreads();
+  for (int64_t k0 = kb; k0 < ke; k0 += BK) {
+    const bool has_next = k0 + BK < ke;
+    if (has_next) load_tile(k0 + BK);
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float fa[TM], fb[TN];
+#pragma unroll
+      for (int g = 0; g < NGM; ++g)
+#pragma unroll
+        for (int i = 0; i < GM; ++i) fa[g * GM + i] = As[buf][kk][g * (BM / NGM) + ty * GM + i];
+#pragma unroll
+      for (int g = 0; g < NGN; ++g)
+#pragma unroll
+        for (int j = 0; j < GN; ++j) fb[g * GN + j] = Bs[buf][kk][g * (BN / NGN) + tx * GN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(fa[i], fb[j], acc[i][j]);
+    }
+    if (has_next) {
+      store_tile(buf ^ 1);
+      __syncthreads();
+      buf ^= 1;
+    }
+  }
+
+  float* out = (splits > 1) ? ws + (int64_t)split * M * N : C;
+#pragma unroll
+  for (int gi = 0; gi < NGM; ++gi)
+#pragma unroll
+    for (int i = 0; i < GM; ++i) {
+      const int64_t m = m0 + gi * (BM / NGM) + ty * GM + i;
+      if (m >= M) continue;
+#pragma unroll
+      for (int gj = 0; gj < NGN; ++gj)
+#pragma unroll
+        for (int j = 0; j < GN; ++j) {
+          const int64_t n = n0 + gj * (BN / NGN) + tx * GN + j;
+          if (n >= N) continue;
+          float v = acc[gi * GM + i][gj * GN + j];
+          if (splits == 1) {
+            if (bias) v += bias[n];
+            v = apply_act(v, act);
+            if (beta) v += out[m * N + n];
+          }
+          out[m * N + n] = v;
+        }
+    }
+}
+
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C,
+                                     const float* __restrict__ bias, int64_t MN, int64_t N,
+                                     int splits, int act, int beta) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= MN) return;
+  float v = 0.f;
+  for (int s = 0; s < splits; ++s) v += ws[(int64_t)s * MN + i];
+  if (bias) v += bias[i % N];
+  v = apply_act(v, act);
+  if (beta) v += C[i];
+  C[i] = v;
+}
+
+// dZ = dY * act'(Y)
+__global__ void act_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dY,
+                               float* __restrict__ dZ, int64_t n, int act) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float y = Y[i], g = dY[i];
+  float r = g;
+  if (act == B200RL_ACT_RELU) r = y > 0.f ? g : 0.f;
+  else if (act == B200RL_ACT_TANH) r = g * (1.f - y * y);
+  dZ[i] = r;
+}
+
+// Column sums of dZ[M,N] in two deterministic stages.
+constexpr int kColRows = 512;  // rows per partial block
+__global__ void colsum_partial_kernel(const float* __restrict__ dZ, float* __restrict__ part,
+                                      int64_t M, int64_t N) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int64_t mb = (int64_t)blockIdx.y * kColRows;
+  const int64_t me = mb + kColRows < M ? mb + kColRows : M;
+  float s = 0.f;
+  for (int64_t m = mb; m < me; ++m) s += dZ[m * N + n];
+  part[(int64_t)blockIdx.y * N + n] = s;
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ db,
+                                    int64_t nparts, int64_t N, int beta) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float s = 0.f;
+  for (int64_t p = 0; p < nparts; ++p) s += part[p * N + n];
+  db[n] = beta ? db[n] + s : s;
+}
+
+// col2im in gather form (deterministic): dX[n,y,x,c] = sum over kernel taps hitting (y,x).
+__global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dX, ConvGeom g,
+                              int64_t total, int Kc) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % g.C);
+  int64_t r = i / g.C;
+  const int x = (int)(r % g.W);
+  r /= g.W;
+  const int y = (int)(r % g.H);
+  const int64_t n = r / g.H;
+  float s = 0.f;
+  for (int ky = 0; ky < g.KH; ++ky) {
+    const int ty = y - ky;
+    if (ty < 0 || ty % g.stride) continue;
+    const int oy = ty / g.stride;
+    if (oy >= g.OH) continue;
+    for (int kx = 0; kx < g.KW; ++kx) {
+      const int tx = x - kx;
+      if (tx < 0 || tx % g.stride) continue;
+      const int ox = tx / g.stride;
+      if (ox >= g.OW) continue;
+      const int64_t pos = (n * g.OH + oy) * g.OW + ox;
+      s += dcol[pos * Kc + (ky * g.KW + kx) * g.C + c];
+    }
+  }
+  dX[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------
+// host-side dispatch
+// ---------------------------------------------------------------------------------------
+struct GemmArgs {
+  float* C;
+  const float* bias;
+  int64_t M, N, K;
+  int act, beta;
+  void* ws;
+  int64_t ws_bytes;
+  cudaStream_t st;
+};
+
+template <int BM, int BN, int TM, int TN, class AL, class BL>
+static int launch_gemm_cfg(const AL& a, const BL& b, const GemmArgs& g) {
+  const int64_t tm = (g.M + BM - 1) / BM, tn = (g.N + BN - 1) / BN;
+  const int64_t tiles = tm * tn;
+  int splits = 1;
+  const int64_t target = 2 * kNumSMs;
+  if (tiles < target && g.K >= 8 * BK && g.ws != nullptr) {
+    int64_t want = (target + tiles - 1) / tiles;
+    int64_t max_by_k = g.K / (4 * BK);
+    int64_t max_by_ws = g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t s = want;
+    if (s > max_by_k) s = max_by_k;
+    if (s > max_by_ws) s = max_by_ws;
+    if (s > 65535) s = 65535;
+    if (s >= 2) splits = (int)s;
+  }
+  int64_t kps = (g.K + splits - 1) / splits;
+  kps = (kps + BK - 1) / BK * BK;
+  splits = (int)((g.K + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  B200RL_CHECK_ARG(tm <= 65535, "gemm: M too large for grid.y (%lld tiles)", (long long)tm);
+  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+  sgemm_kernel<BM, BN, TM, TN, AL, BL><<<grid, 256, 0, g.st>>>(
+      a, b, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws);
+  B200RL_CHECK_LAUNCH("sgemm");
+  if (splits > 1) {
+    const int64_t MN = g.M * g.N;
+    splitk_reduce_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, g.st>>>(
+        (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta);
+    B200RL_CHECK_LAUNCH("splitk_reduce");
+  }
+  return B200RL_OK;
+}
+
+template <class AL, class BL>
+static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
+  if (g.M <= 0 || g.N <= 0) return B200RL_OK;
+  B200RL_CHECK_ARG(g.K > 0, "gemm: K must be > 0");
+  B200RL_CHECK_ARG(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "gemm: dims");
+  if (g.N <= 32) return launch_gemm_cfg<128, 32, 4, 4>(a, b, g);
+  if (g.N <= 64) {
+    if (g.M >= 4096) return launch_gemm_cfg<128, 64, 8, 4>(a, b, g);
+    return launch_gemm_cfg<64, 64, 4, 4>(a, b, g);
+  }
+  const int64_t t128 = ((g.M + 127) / 128) * ((g.N + 127) / 128);
+  if (t128 >= kNumSMs) return launch_gemm_cfg<128, 128, 8, 8>(a, b, g);
+  return launch_gemm_cfg<64, 64, 4, 4>(a, b, g);
+}
+
+static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, void* ws,
+                  int64_t ws_bytes, cudaStream_t st) {
+  const int64_t nparts = (M + kColRows - 1) / kColRows;
+  B200RL_CHECK_ARG(ws != nullptr && ws_bytes >= (int64_t)(nparts * N * sizeof(float)),
+                   "bias gradient needs %lld bytes of workspace",
+                   (long long)(nparts * N * sizeof(float)));
+  dim3 grid((unsigned)((N + 127) / 128), (unsigned)nparts);
+  colsum_partial_kernel<<<grid, 128, 0, st>>>(dZ, (float*)ws, M, N);
+  B200RL_CHECK_LAUNCH("colsum_partial");
+  colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)ws, db, nparts,
+                                                                   N, beta);
+  B200RL_CHECK_LAUNCH("colsum_final");
+  return B200RL_OK;
+}
+
+static int make_geom(const b200rl_conv_t* c, ConvGeom& g) {
+  B200RL_CHECK_ARG(c != nullptr, "conv geometry is NULL");
+  B200RL_CHECK_ARG(c->N > 0 && c->H > 0 && c->W > 0 && c->C > 0 && c->KH > 0 && c->KW > 0 &&
+                       c->F > 0 && c->stride > 0,
+                   "conv: non-positive dimension");
+  B200RL_CHECK_ARG(c->H >= c->KH && c->W >= c->KW, "conv: kernel larger than input");
+  g.H = c->H; g.W = c->W; g.C = c->C; g.KH = c->KH; g.KW = c->KW; g.F = c->F;
+  g.stride = c->stride;
+  g.OH = (c->H - c->KH) / c->stride + 1;
+  g.OW = (c->W - c->KW) / c->stride + 1;
+  g.d_ohow = FastDiv((uint32_t)(g.OH * g.OW));
+  g.d_ow = FastDiv((uint32_t)g.OW);
+  g.d_kwc = FastDiv((uint32_t)(g.KW * g.C));
+  g.in_row = (int64_t)c->W * c->C;
+  g.in_img = c->x_batch_stride > 0 ? c->x_batch_stride : (int64_t)c->H * c->W * c->C;
+  const int64_t M = (int64_t)c->N * g.OH * g.OW;
+  B200RL_CHECK_ARG(M < (1ll << 31), "conv: too many output positions");
+  return B200RL_OK;
+}
+
+}  // namespace b200rl
+
+using namespace b200rl;
+
+extern "C" {
+
+int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y,
+                     int64_t M, int64_t K, int64_t N, int act, void* workspace,
+                     int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X && W && Y, "dense_fwd: NULL argument");
+  B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_fwd: ldx < K");
+  GemmArgs g{Y, bias, M, N, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  return launch_gemm(ARow{X, ldx ? ldx : K}, BRow{W, N}, g);
+}
+
+int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
+                     float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
+                     void* workspace, int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X && W && dY && dW, "dense_bwd: NULL argument");
+  B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_bwd: ldx < K");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (dX) {
+    GemmArgs g{dX, nullptr, M, K, N, B200RL_ACT_NONE, 0, workspace, ws_bytes, st};
+    rc = launch_gemm(ARow{dY, N}, BCol{W, N}, g);
+    if (rc) return rc;
+  }
+  {
+    GemmArgs g{dW, nullptr, K, N, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
+    rc = launch_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g);
+    if (rc) return rc;
+  }
+  if (db) {
+    rc = colsum(dY, db, M, N, accumulate, workspace, ws_bytes, st);
+    if (rc) return rc;
+  }
+  return B200RL_OK;
+}
+
+int b200rl_act_bwd(const float* Y, const float* dY, float* dZ, int64_t n, int act,
+                   void* stream) {
+  B200RL_CHECK_ARG(Y && dY && dZ && n >= 0, "act_bwd: bad argument");
+  if (n == 0) return B200RL_OK;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, dY, dZ, n, act);
+  B200RL_CHECK_LAUNCH("act_bwd");
+  return B200RL_OK;
+}
+
+int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
+                      const float* bias, float* Y, const b200rl_conv_t* c, int act,
+                      void* workspace, int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X && Wt && Y, "conv2d_fwd: NULL argument");
+  ConvGeom cg;
+  int rc = make_geom(c, cg);
+  if (rc) return rc;
+  const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
+  GemmArgs g{Y, bias, M, c->F, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  if (x_is_u8) {
+    AConv<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
+    return launch_gemm(a, BRow{Wt, c->F}, g);
+  }
+  AConv<float> a{ConvView<float>{(const float*)X, cg, 1.f}};
+  return launch_gemm(a, BRow{Wt, c->F}, g);
+}
+
+int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
+                      const float* dY, float* dX, float* dW, float* db,
+                      const b200rl_conv_t* c, int accumulate, void* workspace,
+                      int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X && Wt && dY && dW, "conv2d_bwd: NULL argument");
+  B200RL_CHECK_ARG(!(dX && x_is_u8), "conv2d_bwd: no input gradient for u8 input");
+  ConvGeom cg;
+  int rc = make_geom(c, cg);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
+  const int64_t F = c->F;
+  {  // dW[K,F] = im2col(X)^T @ dY
+    GemmArgs g{dW, nullptr, K, F, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
+    if (x_is_u8) {
+      AConvT<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
+      rc = launch_gemm(a, BRow{dY, F}, g);
+    } else {
+      AConvT<float> a{ConvView<float>{(const float*)X, cg, 1.f}};
+      rc = launch_gemm(a, BRow{dY, F}, g);
+    }
+    if (rc) return rc;
+  }
+  if (db) {
+    rc = colsum(dY, db, M, F, accumulate, workspace, ws_bytes, st);
+    if (rc) return rc;
+  }
+  if (dX) {  // dcol[M,K] = dY @ W^T, then gather-form col2im
+    const int64_t need = M * K * (int64_t)sizeof(float);
+    B200RL_CHECK_ARG(workspace && ws_bytes >= need,
+                     "conv2d_bwd: input gradient needs %lld bytes of workspace",
+                     (long long)need);
+    GemmArgs g{(float*)workspace, nullptr, M, K, F, B200RL_ACT_NONE, 0, nullptr, 0, st};
+    rc = launch_gemm(ARow{dY, F}, BCol{Wt, F}, g);
+    if (rc) return rc;
+    const int64_t total = (int64_t)c->N * c->H * c->W * c->C;
+    col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, dX, cg,
+                                                                   total, (int)K);
+    B200RL_CHECK_LAUNCH("col2im");
+  }
+  return B200RL_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,208 @@
+"""Network base class (tf_agents/networks/network.py:111).
+
+A Network owns ONE flat fp32 parameter buffer and ONE flat gradient buffer on its device;
+layers hold views.  `__call__(observation, step_type=None, network_state=(), training=False)`
+returns `(output, network_state)` like the reference; `forward_train` additionally records
+the activations needed by `backward`.
+"""
+import copy as _copy
+
+import numpy as np
+import torch
+
+from agents_b200.networks import layers as layers_lib
+from agents_b200.utils import nest
+
+
+class Network(object):
+
+  def __init__(self, input_tensor_spec=None, state_spec=(), name=None, device='cuda'):
+    self._input_tensor_spec = input_tensor_spec
+    self._state_spec = state_spec
+    self._name = name or type(self).__name__
+    self._device = torch.device(device)
+    self._layers = []
+    self._built = False
+    self._params = None
+    self._grads = None
+    self._seed = None
+
+  # ---- reference surface ------------------------------------------------------------------
+  @property
+  def name(self):
+    return self._name
+
+  @property
+  def input_tensor_spec(self):
+    return self._input_tensor_spec
+
+  @property
+  def state_spec(self):
+    return self._state_spec
+
+  @property
+  def device(self):
+    return self._device
+
+  @property
+  def layers(self):
+    return list(self._layers)
+
+  def create_variables(self, input_tensor_spec=None, **kwargs):
+    """Builds parameters for `input_tensor_spec`; returns the output spec
+    (network.py `create_variables`)."""
+    from agents_b200.specs import tensor_spec
+    if input_tensor_spec is not None:
+      if self._input_tensor_spec is None:
+        self._input_tensor_spec = input_tensor_spec
+    if not self._built:
+      if self._input_tensor_spec is None:
+        raise ValueError('Network needs an input_tensor_spec to create its variables.')
+      self._build(nest.flatten(self._input_tensor_spec)[0].shape)
+    return tensor_spec.TensorSpec(self._output_shape, torch.float32)
+
+  @property
+  def variables(self):
+    self._require_built()
+    return list(self._param_views)
+
+  @property
+  def trainable_weights(self):
+    return self.variables
+
+  @property
+  def non_trainable_weights(self):
+    return []
+
+  @property
+  def trainable_variables(self):
+    return self.variables
+
+  @property
+  def losses(self):
+    """Regularisation losses as (coef, tensor) pairs (Keras `layer.losses`)."""
+    out = []
+    for l in self._layers:
+      if getattr(l, 'l2', 0.0):
+        out.append((l.l2, l.kernel))
+    return out
+
+  def copy(self, **kwargs):
+    """Same architecture, freshly allocated variables (network.py `copy`)."""
+    new = _copy.copy(self)
+    new._layers = [_copy.copy(l) for l in self._layers]
+    new._built = False
+    new._params = None
+    new._grads = None
+    if 'name' in kwargs:
+      new._name = kwargs['name']
+    if self._built:
+      new._build(self._input_shape)
+    return new
+
+  # ---- flat storage -----------------------------------------------------------------------
+  @property
+  def flat_params(self):
+    self._require_built()
+    return self._params
+
+  @property
+  def flat_grads(self):
+    self._require_built()
+    return self._grads
+
+  @property
+  def param_offsets(self):
+    """int64 offsets [n_vars+1] of each variable inside the flat buffer."""
+    self._require_built()
+    return self._offsets
+
+  def _require_built(self):
+    if not self._built:
+      self.create_variables()
+
+  def set_seed(self, seed):
+    self._seed = seed
+    return self
+
+  def _build(self, input_shape):
+    shape = tuple(int(d) for d in input_shape)
+    self._input_shape = shape
+    sizes = []
+    pending_div = None
+    for l in self._layers:
+      if isinstance(l, layers_lib.CastScale):
+        pending_div = l.divisor
+        shape = l.build(shape)
+        continue
+      if pending_div is not None:
+        if not isinstance(l, layers_lib.Conv2D):
+          raise ValueError('CastScale must be followed by a Conv2D layer (it is fused into it).')
+        l.pre_divisor = pending_div
+        pending_div = None
+      shape = l.build(shape)
+      for ps in l.param_shapes():
+        sizes.append(int(np.prod(ps)))
+    self._output_shape = shape
+    total = int(sum(sizes))
+    # pad each variable to 4 floats so views stay 16 B aligned
+    offs = [0]
+    for s in sizes:
+      offs.append(offs[-1] + (s + 3) // 4 * 4)
+    self._params = torch.zeros(max(offs[-1], 4), dtype=torch.float32, device=self._device)
+    self._grads = torch.zeros_like(self._params)
+    self._offsets = offs
+    self._param_views = []
+    self._grad_views = []
+    i = 0
+    for l in self._layers:
+      shapes = l.param_shapes()
+      if not shapes:
+        continue
+      pv, gv = [], []
+      for ps in shapes:
+        n = int(np.prod(ps))
+        pv.append(self._params[offs[i]:offs[i] + n].view(ps))
+        gv.append(self._grads[offs[i]:offs[i] + n].view(ps))
+        i += 1
+      l.bind(pv, gv)
+      self._param_views.extend(pv)
+      self._grad_views.extend(gv)
+    self._n_params = total
+    gen = None
+    if self._seed is not None:
+      gen = torch.Generator().manual_seed(int(self._seed))
+    with torch.no_grad():
+      for l in self._layers:
+        if l.has_params:
+          l.init_params(gen)
+    self._built = True
+
+  # ---- execution --------------------------------------------------------------------------
+  def _run(self, x, keep):
+    self._require_built()
+    tape = []
+    for l in self._layers:
+      if isinstance(l, layers_lib.CastScale):
+        continue
+      y = l.forward(x)
+      if keep:
+        tape.append((l, x, y))
+      x = y
+    return x, tape
+
+  def __call__(self, observation, step_type=None, network_state=(), training=False):
+    out, _ = self._run(observation, keep=False)
+    return out, network_state
+
+  def forward_train(self, observation):
+    """Forward that records activations; returns (output, tape)."""
+    return self._run(observation, keep=True)
+
+  def backward(self, tape, dy):
+    """Back-propagates dLoss/d(output) through `tape`, OVERWRITING flat_grads."""
+    first = next(i for i, (l, _, _) in enumerate(tape) if l.has_params)
+    for i in range(len(tape) - 1, -1, -1):
+      l, x, y = tape[i]
+      dy = l.backward(x, y, dy, need_dx=i > first)
+    return self._grads

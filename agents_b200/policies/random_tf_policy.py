@@ -1,0 +1,2 @@
+"""Module alias matching tf_agents/policies/random_tf_policy.py; see q_policy.py in this package."""
+from agents_b200.policies.q_policy import *  # noqa: F401,F403

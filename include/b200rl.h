@@ -1,0 +1,262 @@
+/*
+ * b200rl.h — C ABI of libb200rl.so: the collect -> store -> sample -> update hot path
+ * of TF-Agents, as hand-written sm_100a CUDA.
+ *
+ * The reference (tensorflow/agents @ eb24cf5f) has no FFI for this path: it is plain
+ * Python over TensorFlow ops.  This header therefore *defines* the
+ * boundary a reference maintainer would bind with ctypes; every
+ * entry point cites the reference function whose device work it replaces.  All
+ * file:line citations are relative to /root/reference/tf_agents/.
+ *
+ * Conventions
+ *   - Every pointer named *_dev / documented "device" is a CUDA device pointer owned by the
+ *     caller (PyTorch in this repo).  The library never allocates persistent memory.
+ *   - `stream` is a cudaStream_t passed as void*.  Every call only ENQUEUES work on that
+ *     stream and returns; ordering on one stream replaces the reference's
+ *     tf.CriticalSection (replay_buffers/tf_uniform_replay_buffer.py:154,582-601).
+ *   - Return value: 0 = ok, <0 = error; b200rl_last_error() gives the message
+ *     (thread-local).  No entry point falls back to the CPU.
+ *   - Counters that the reference keeps in tf.Variables (last_id, train_step, Periodically
+ *     counter, optimizer iterations) live in device memory so that a whole
+ *     collect/train step can be captured in one CUDA graph and replayed.  Counter blocks
+ *     named step_dev / counter_dev (int64[2]) and the rng_call_dev of the env / policy
+ *     kernels (uint64[2]) are {value, ticket}: the second word is scratch for the
+ *     last-block-done update and must start at 0.  b200rl_rb_sample / b200rl_rb_draw use
+ *     ring->ticket instead, so their rng_call_dev is a single uint64.
+ */
+#ifndef B200RL_H_
+#define B200RL_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RL_OK 0
+#define B200RL_ERR_INVALID (-1)
+#define B200RL_ERR_CUDA (-2)
+#define B200RL_ERR_UNSUPPORTED (-3)
+
+#define B200RL_MAX_LEAVES 24
+
+/* activation codes for dense / conv epilogues */
+#define B200RL_ACT_NONE 0
+#define B200RL_ACT_RELU 1
+#define B200RL_ACT_TANH 2
+
+/* element-wise TD loss kinds (utils/common.py:1199-1208) */
+#define B200RL_LOSS_HUBER 0
+#define B200RL_LOSS_SQUARED 1
+
+const char* b200rl_last_error(void);
+int b200rl_version(void);
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t b200rl_launch_count(void);
+
+/* ------------------------------------------------------------------------------------
+ * Ring storage — replaces Table (replay_buffers/table.py:32-137) + the variables of
+ * TFUniformReplayBuffer (replay_buffers/tf_uniform_replay_buffer.py:132-161).
+ * One leaf == one slot of the Table: a [capacity, row_bytes] byte matrix.
+ * Segment b occupies rows [b*max_length, (b+1)*max_length).
+ * ------------------------------------------------------------------------------------ */
+typedef struct {
+  void* storage;     /* device, [capacity * row_bytes] bytes */
+  int64_t row_bytes; /* bytes of one item of this leaf */
+} b200rl_leaf_t;
+
+typedef struct {
+  int32_t num_leaves;
+  int32_t _pad;
+  int64_t batch_size; /* B_env: number of segments */
+  int64_t max_length; /* L: rows per segment */
+  int64_t* id_table;  /* device, [capacity] int64 (id table, tf_uniform_replay_buffer.py:152) */
+  int64_t* last_id;   /* device scalar int64, -1 when empty (:153) */
+  uint32_t* ticket;   /* device scalar uint32 scratch, zero-initialised by the caller */
+  b200rl_leaf_t leaves[B200RL_MAX_LEAVES];
+} b200rl_ring_t;
+
+/* _add_batch (tf_uniform_replay_buffer.py:182-209): id = ++last_id; rows[b] = b*L + id % L;
+ * scatter every leaf row and the id.  items[i] is a device pointer to [B_env, row_bytes_i]. */
+int b200rl_rb_add_batch(const b200rl_ring_t* ring, const void* const* items, void* stream);
+
+/* _get_next (tf_uniform_replay_buffer.py:211-310), time_stacked form.
+ *   B = sample_batch_size (>=1; pass 1 for the unbatched form), T = num_steps (>=1).
+ *   ids_dev/offs_dev: when both non-NULL the kernel uses these externally supplied draws
+ *     (ids in [min,max), offs in [0,B_env)) — "oracle mode"; otherwise it draws with
+ *     Philox4x32-10 keyed by `seed`, call index *rng_call_dev (then increments it).
+ *   out[i]: device pointer to [B, T, row_bytes_i]; out_ids: [B,T] int64 (id table values);
+ *   out_rows: optional [B,T] int64 row indices; out_prob: [B] f32.
+ *   status_dev: optional device int32, set to 1 when the valid id range is empty. */
+int b200rl_rb_sample(const b200rl_ring_t* ring, int64_t B, int64_t T, const int64_t* ids_dev,
+                     const int64_t* offs_dev, uint64_t seed, uint64_t* rng_call_dev,
+                     void* const* out, int64_t* out_ids, int64_t* out_rows, float* out_prob,
+                     int32_t* status_dev, void* stream);
+
+/* Table.read(rows) (table.py:86-110) for explicit row ids rows_dev[n] (already < capacity). */
+int b200rl_rb_read_rows(const b200rl_ring_t* ring, const int64_t* rows_dev, int64_t n,
+                        void* const* out, int64_t* out_ids, void* stream);
+
+/* Table.write(rows, values) (table.py:112-137) for explicit row ids. */
+int b200rl_rb_write_rows(const b200rl_ring_t* ring, const int64_t* rows_dev, int64_t n,
+                         const void* const* items, void* stream);
+
+/* _gather_all (tf_uniform_replay_buffer.py:533-557): out[i] is [B_env, n_valid, row_bytes_i],
+ * items in age order; n_valid is the host's copy of max_val-min_val. */
+int b200rl_rb_gather_all(const b200rl_ring_t* ring, int64_t n_valid, void* const* out,
+                         void* stream);
+
+/* _clear (tf_uniform_replay_buffer.py:559-579): last_id = -1; zero tables when clear_all. */
+int b200rl_rb_clear(const b200rl_ring_t* ring, int clear_all, void* stream);
+
+/* Philox draw alone (tf_uniform_replay_buffer.py:265-272) — same stream as b200rl_rb_sample. */
+int b200rl_rb_draw(const b200rl_ring_t* ring, int64_t B, int64_t T, uint64_t seed,
+                   uint64_t* rng_call_dev, int64_t* out_ids, int64_t* out_offs, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Scans — utils/value_ops.py
+ * ------------------------------------------------------------------------------------ */
+/* discounted_return (value_ops.py:21-99).  Inputs [T,B] when time_major else [B,T].
+ * final_value may be NULL (zeros).  provide_all: out has the input layout; else out is [B]. */
+int b200rl_discounted_return(const float* rewards, const float* discounts,
+                             const float* final_value, float* out, int64_t B, int64_t T,
+                             int time_major, int provide_all, void* stream);
+
+/* generalized_advantage_estimation (value_ops.py:102-164). */
+int b200rl_gae(const float* values, const float* final_value, const float* discounts,
+               const float* rewards, float td_lambda, float* out_adv, int64_t B, int64_t T,
+               int time_major, void* stream);
+
+/* to_n_step_transition reward/discount reduction (trajectories/trajectory.py:815-832):
+ * reward,discount are [B,T] (T = n+1, last column ignored). */
+int b200rl_nstep_reduce(const float* reward, const float* discount, double gamma,
+                        float* out_reward, float* out_discount, int64_t B, int64_t T,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * DQN loss epilogue — agents/dqn/dqn_agent.py:462-579 (+ :75-78, :451-460, :604-645,
+ * DdqnAgent :659-700), utils/common.py:367-411 (index_with_actions), :1199-1208 (losses),
+ * :1400-1476 (aggregate_losses).
+ *   q[B,A]          online Q(s_0)
+ *   next_q_tgt[B,A] target Q(s_n)          (value taken here)
+ *   next_q_sel[B,A] net that picks argmax  (== next_q_tgt for DQN, online Q(s_n) for DDQN)
+ *   next_mask[B,A]  optional int32 action mask for the argmax (1 = allowed)
+ *   step_type0[B]   int32 step type of the first frame (LAST=2 zeroes the loss)
+ *   traj_reward/traj_discount [B,T] raw trajectory fields (T = n+1); n-step reduction fused.
+ *   weights[B] optional.  global_batch: divisor of the loss sum (B * replicas).
+ * Outputs: loss[0] (= sum(td_loss*w)/global_batch, no reg), td_loss[B], td_error[B],
+ *          dq[B,A] = dLoss/dq (zero except at the taken action), nan_flag (optional int32,
+ *          set when loss is not finite; dqn_agent.py:422 check_numerics).
+ * ------------------------------------------------------------------------------------ */
+int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt, const float* next_q_sel,
+                       const int32_t* next_mask, const int32_t* actions,
+                       const int32_t* step_type0, const float* traj_reward,
+                       const float* traj_discount, const float* weights, int64_t B, int64_t A,
+                       int64_t T, double gamma, double reward_scale, int loss_kind,
+                       float global_batch, float* loss, float* td_loss, float* td_error,
+                       float* dq, int32_t* nan_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Network layers (fp32).  Replace Keras Dense/Conv2D fwd+bwd that the reference executes
+ * through TensorFlow (networks/encoding_network.py:224-312, q_network.py:126-135).
+ * All matrices are row-major.
+ * ------------------------------------------------------------------------------------ */
+/* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
+ * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of
+ * ws_bytes (may be NULL when ws_bytes==0; then split-K is disabled). */
+int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y,
+                     int64_t M, int64_t K, int64_t N, int act, void* workspace,
+                     int64_t ws_bytes, void* stream);
+/* Given dY[M,N] (already multiplied by act'), compute dX[M,K] (optional, NULL to skip),
+ * dW[K,N] and db[N].  accumulate!=0 adds into dW/db instead of overwriting. */
+int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
+                     float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
+                     void* workspace, int64_t ws_bytes, void* stream);
+/* dZ = dY * act'(Y) element-wise (in place allowed). */
+int b200rl_act_bwd(const float* Y, const float* dY, float* dZ, int64_t n, int act,
+                   void* stream);
+
+/* conv2d, NHWC, VALID padding, square stride.  X is [N,H,W,C] f32, or u8 when x_is_u8
+ * (then each element is converted to f32 and DIVIDED by x_scale — the reference's
+ * cast+/255 preprocessing layer, examples/dqn/mnih15/dqn_train_eval_atari.py:104).
+ * Wt is [KH,KW,C,F] (Keras HWIO), Y is [N,OH,OW,F]. */
+typedef struct {
+  int32_t N, H, W, C, KH, KW, F, stride;
+  int64_t x_batch_stride; /* elements between consecutive images of X (0 -> H*W*C) */
+} b200rl_conv_t;
+int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
+                      const float* bias, float* Y, const b200rl_conv_t* g, int act,
+                      void* workspace, int64_t ws_bytes, void* stream);
+int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
+                      const float* dY, float* dX, float* dW, float* db,
+                      const b200rl_conv_t* g, int accumulate, void* workspace,
+                      int64_t ws_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimisers and target updates on flat fp32 parameter buffers.
+ * ------------------------------------------------------------------------------------ */
+/* TF Adam (tf.compat.v1.train.AdamOptimizer / Keras Adam):
+ *   t = ++(*step_dev); lr_t = lr*sqrt(1-b2^t)/(1-b1^t);
+ *   m = b1*m+(1-b1)*g; v = b2*v+(1-b2)*g*g; p -= lr_t*m/(sqrt(v)+eps).
+ * grad_scale multiplies g first (1.0 normally; used for global-norm clipping when
+ * grad_scale_dev != NULL, in which case *grad_scale_dev is read on device). */
+int b200rl_adam_tf(float* p, const float* g, float* m, float* v, int64_t n, float lr,
+                   float b1, float b2, float eps, int64_t* step_dev,
+                   const float* grad_scale_dev, void* stream);
+/* TF RMSProp (tf.compat.v1.train.RMSPropOptimizer; Mnih'15 config
+ * examples/dqn/mnih15/dqn_train_eval_atari.py:176-182): centered optional. */
+int b200rl_rmsprop_tf(float* p, const float* g, float* ms, float* mg, float* mom, int64_t n,
+                      float lr, float decay, float momentum, float eps, int centered,
+                      const float* grad_scale_dev, void* stream);
+/* soft_variables_update (utils/common.py:250-346): t = (1-tau)*t + tau*s, gated on device by
+ * Periodically (utils/common.py:450-507): if period>1 the kernel does
+ * c = ++(*counter_dev); update only when c % period == 0.  period<=1: always. */
+int b200rl_soft_update(float* target, const float* source, int64_t n, float tau,
+                       int64_t period, int64_t* counter_dev, void* stream);
+/* Per-variable clip_by_norm (utils/eager_utils.py:227-246): segments given by
+ * offsets[nseg+1] (device int64). */
+int b200rl_clip_by_norm_segments(float* g, const int64_t* offsets_dev, int64_t nseg,
+                                 float max_norm, void* stream);
+/* tf.clip_by_global_norm scale factor: *scale_dev = clip/max(norm,clip); *norm_dev=norm. */
+int b200rl_global_norm_scale(const float* g, int64_t n, float clip, float* scale_dev,
+                             float* norm_dev, void* workspace, int64_t ws_bytes,
+                             void* stream);
+/* Generic helpers used by the host glue. */
+int b200rl_add_scaled(float* dst, const float* src, int64_t n, float alpha, void* stream);
+int b200rl_l2_sum(const float* x, int64_t n, float coef, float* out_accum, void* stream);
+int b200rl_counter_add(int64_t* counter_dev, int64_t inc, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Collect — environments + policies
+ * ------------------------------------------------------------------------------------ */
+/* EpsilonGreedyPolicy._action (policies/epsilon_greedy_policy.py:120-145) over
+ * GreedyPolicy(QPolicy) (greedy_policy.py:70-89, q_policy.py:150-194):
+ *   a = (u >= eps) ? argmax_a q[b,a] (masked) : uniform{0..A-1 | mask}.  u, random action from
+ *   Philox (seed, *rng_call_dev, element b); when u_dev/rand_dev are non-NULL they are used
+ *   instead (oracle mode). */
+int b200rl_epsilon_greedy(const float* q, const int32_t* mask, int64_t B, int64_t A, float eps,
+                          uint64_t seed, uint64_t* rng_call_dev, const float* u_dev,
+                          const int32_t* rand_dev, int32_t* out_action, void* stream);
+
+/* RandomTFEnvironment-style synthetic env (environments/random_tf_environment.py:96-129)
+ * with per-env termination and the TFEnvironment auto-reset contract
+ * (environments/tf_environment.py:211-241; trajectories/time_step.py:135-195):
+ *   if step_type[b]==LAST: -> FIRST, reward 0, discount 1, fresh obs
+ *   else: reward~U[0,1), terminate w.p. p_term -> LAST/discount 0 else MID/discount 1.
+ * obs is [B, obs_bytes] u8 (uniform 0..255) when obs_is_u8 else [B, obs_elems] f32 ~ N(0,1).
+ * State (step_type) is read and written in place. */
+int b200rl_env_random_step(int32_t* step_type, void* obs, int64_t obs_elems, int obs_is_u8,
+                           float* reward, float* discount, int64_t B, float p_term,
+                           uint64_t seed, uint64_t* rng_call_dev, void* stream);
+
+/* Vectorised CartPole-v1 dynamics (gym classic_control formulae; the reference loads it via
+ * suite_gym, agents/dqn/examples/v2/train_eval.py:151): state[B,4] f32, steps[B] int32. */
+int b200rl_env_cartpole_step(float* state, int32_t* steps, int32_t* step_type,
+                             const int32_t* action, float* obs, float* reward, float* discount,
+                             int64_t B, int32_t max_steps, uint64_t seed,
+                             uint64_t* rng_call_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RL_H_ */
