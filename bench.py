@@ -1,0 +1,406 @@
+"""bench.py — train steps/sec (DQN Atari-shape, batch 256) on N B200s, replay GB/s.
+
+Workload (BASELINE.json configs[1]): synthetic Atari-shape observations 84x84x4 uint8, a
+1 048 576-slot TFUniformReplayBuffer (256 segments x 4096) per GPU, sample batch 256 x T=2,
+Mnih'15 Q-network, Huber loss, centered RMSProp (examples/dqn/mnih15 config), gamma 0.99, hard
+target update every 2500 steps.  One "step" = get_next(256, 2) + DqnAgent.train(experience).
+
+  value        steps/s with the ring resident in HBM; the step is replayed as ONE CUDA graph.
+  e2e          the same step through the public API with HOST buffers: every step copies one
+               driver step of collected frames (256 x 28 244 B) from pinned host memory,
+               add_batch, get_next, train, and reads the loss back.
+  roofline     the update's GEMM/conv work (the dominant share of the step) against the measured
+               tensor peak; roofline_gather: the replay gather kernel against measured HBM GB/s.
+  cpu_baseline the torch-CPU restatement of the reference train step (oracle/dqn_torch.py) on
+               the host cores (TensorFlow is not installable here).
+
+`--impl reference` times that CPU restatement alone (the reference arm of the contract).
+N>1 (torchrun): one process per GPU, each with its own 1M-slot ring shard and a local batch of
+256; gradients are SUM-all-reduced (NCCL) every step, loss is divided by the global batch
+(utils/common.py:1465-1467).  value = batch-256-equivalent train steps/s of the whole job
+(weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+ROW_BYTES = 4 + 28224 + 4 + 4 + 4 + 4          # Atari-shape Trajectory row
+A = 6
+B, T = 256, 2
+B_ENV, L = 256, 4096
+CONV = ((32, 8, 4), (64, 4, 2), (64, 3, 1))
+FC = (512,)
+# Mnih'15 net forward = 9.35 M MAC/sample; step = fwd(s0) + fwd_target(sn) + bwd(2x)
+FLOPS_PER_STEP = 4 * 2 * 9.35e6 * B
+GATHER_BYTES = 2 * B * T * ROW_BYTES + 8 * B * T
+
+
+def _peaks():
+  p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+  if os.path.exists(p):
+    d = json.load(open(p))
+    return dict(hbm=d['hbm_gbs'], tensor_burst=d['bf16_tflops'],
+                tensor=d.get('bf16_tflops_sustained', d['bf16_tflops']), src='measured')
+  return dict(hbm=6650.0, tensor_burst=1590.0, tensor=1400.0, src='fallback')
+
+
+def _mnih_layers(rng):
+  """numpy parameter dicts of the Mnih'15 net (for the CPU arm)."""
+  layers = [dict(kind='cast_scale', divisor=255.0)]
+  c_in, hw = 4, 84
+  for f, k, s in CONV:
+    fan = k * k * c_in
+    layers.append(dict(kind='conv', w=(rng.randn(k, k, c_in, f) * np.sqrt(2.0 / fan)).astype(np.float32),
+                       b=np.zeros(f, np.float32), stride=s, act='relu'))
+    c_in, hw = f, (hw - k) // s + 1
+  layers.append(dict(kind='flatten'))
+  n_in = hw * hw * c_in
+  for u in FC:
+    layers.append(dict(kind='dense', w=(rng.randn(n_in, u) * np.sqrt(2.0 / n_in)).astype(np.float32),
+                       b=np.zeros(u, np.float32), act='relu'))
+    n_in = u
+  layers.append(dict(kind='dense', w=(rng.rand(n_in, A) * 0.06 - 0.03).astype(np.float32),
+                     b=np.full(A, -0.2, np.float32), act=None))
+  return layers
+
+
+def cpu_reference_steps(steps, warmup, seed=0):
+  """Times the CPU restatement: sample (numpy ring gather) + train (torch CPU).  Returns
+  (steps_per_s, cores, sample_description)."""
+  import torch
+  from oracle import dqn_torch
+  from oracle import replay as oreplay
+  cores = os.cpu_count() or 1
+  torch.set_num_threads(cores)
+  rng = np.random.RandomState(seed)
+  b_env, l = 64, 256                          # 16 384-slot ring (0.46 GB) on the host
+  shapes = [(), (84, 84, 4), (), (), (), ()]
+  dtypes = [np.int32, np.uint8, np.int32, np.int32, np.float32, np.float32]
+  ring = oreplay.UniformReplayOracle(shapes, dtypes, b_env, l, seed=seed)
+  ring.storage[1][...] = rng.randint(0, 256, size=ring.storage[1].shape, dtype=np.uint8)
+  ring.storage[0][...] = rng.randint(0, 3, size=ring.capacity)
+  ring.storage[2][...] = rng.randint(0, A, size=ring.capacity)
+  ring.storage[4][...] = rng.rand(ring.capacity)
+  ring.storage[5][...] = (rng.rand(ring.capacity) > 0.1)
+  ring.last_id = 2 * l + 17
+  agent = dqn_torch.DqnTorchOracle(_mnih_layers(rng))
+
+  def one():
+    data, _, _, _ = ring.get_next(B, T)
+    return agent.train(dict(step_type=data[0], observation=data[1], action=data[2],
+                            reward=data[4], discount=data[5]))
+
+  for _ in range(warmup):
+    one()
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    one()
+  dt = time.perf_counter() - t0
+  sample = (f'{steps} train steps (batch {B}, T={T}, Mnih15 net, torch-CPU restatement, '
+            f'{b_env}x{l}-slot host ring instead of 1M slots)')
+  return steps / dt, cores, sample
+
+
+class ClockSampler(object):
+  Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+       'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+       'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+  def __init__(self, index):
+    self.index = index
+    self.proc = None
+    self.path = f'/tmp/b200rl_clocks_{os.getpid()}.csv'
+
+  def start(self):
+    try:
+      self.f = open(self.path, 'w')
+      self.proc = subprocess.Popen(
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+           '-i', str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
+    except Exception:
+      self.proc = None
+
+  def stop(self):
+    out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[])
+    if self.proc is None:
+      return out
+    self.proc.terminate()
+    try:
+      self.proc.wait(timeout=5)
+    except Exception:
+      self.proc.kill()
+    self.f.close()
+    sm, mx, reasons = [], [], set()
+    names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+    for line in open(self.path):
+      p = [x.strip() for x in line.split(',')]
+      if len(p) < 9:
+        continue
+      try:
+        sm.append(float(p[1]))
+        mx.append(float(p[2]))
+      except ValueError:
+        continue
+      for n, v in zip(names, p[5:9]):
+        if v.lower().startswith('active'):
+          reasons.add(n)
+    if sm:
+      out = dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                 samples=len(sm))
+    try:
+      os.remove(self.path)
+    except OSError:
+      pass
+    return out
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  steps = max(1, min(args.steps, 20))
+  sps, cores, sample = cpu_reference_steps(steps, min(args.warmup, 2))
+  line = dict(
+      impl='reference', metric='train steps/sec (DQN Atari-shape, batch 256)', value=sps,
+      unit='steps/s', n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2),
+      ms_per_step=1000.0 / sps, higher_is_better=True, scaling='weak', vs_baseline=None,
+      dtype='f32', data='synthetic',
+      config=dict(workload='DQN synthetic Atari-shape obs 84x84x4 uint8, batch 256, T=2, '
+                           'Mnih15 net, Huber, RMSProp', global_batch=B, parallelism='cpu'),
+      cpu_baseline=dict(value=sps, unit='steps/s', cores=cores, kind='port', sample=sample),
+      e2e=dict(value=sps, unit='steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=200)
+  ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--impl', default='b200')
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  ap.add_argument('--no-graph', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    return run_reference(args)
+
+  import torch
+  import torch.distributed as dist
+  from agents_b200 import _lib
+  from agents_b200 import optimizers
+  from agents_b200.agents.dqn import dqn_agent
+  from agents_b200.networks import layers as Ly
+  from agents_b200.networks import q_network
+  from agents_b200.replay_buffers import tf_uniform_replay_buffer as rb_mod
+  from agents_b200.specs import tensor_spec
+  from agents_b200.trajectories import time_step as ts
+  from agents_b200.trajectories import trajectory
+  from agents_b200.utils import common
+
+  if not torch.cuda.is_available():
+    raise SystemExit('bench.py needs a CUDA device: the hot path has no CPU fallback.')
+  rank = int(os.environ.get('RANK', '0'))
+  local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  torch.cuda.set_device(local_rank)
+  dev = torch.device('cuda', local_rank)
+  if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+  W = max(args.warmup, 3)
+  K = args.steps
+  peaks = _peaks()
+
+  # ---- build the workload ---------------------------------------------------------------------
+  obs_spec = tensor_spec.TensorSpec((84, 84, 4), torch.uint8, 'observation')
+  act_spec = tensor_spec.BoundedTensorSpec((), torch.int32, 0, A - 1, 'action')
+  net = q_network.QNetwork(obs_spec, act_spec, preprocessing_layers=Ly.CastScale(255.),
+                           conv_layer_params=CONV, fc_layer_params=FC, device=dev).set_seed(0)
+  opt = optimizers.RMSPropOptimizer(2.5e-4, decay=0.95, momentum=0.0, epsilon=1e-5, centered=True)
+  agent = dqn_agent.DqnAgent(ts.time_step_spec(obs_spec), act_spec, q_network=net, optimizer=opt,
+                             epsilon_greedy=0.01, n_step_update=1, target_update_tau=1.0,
+                             target_update_period=2500, gamma=0.99, seed=0x5eed0000 + rank)
+  agent.initialize()
+  if world > 1:
+    agent.replicas = world
+    agent._grad_sync = lambda g: dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    dist.broadcast(net.flat_params, 0)
+    dist.broadcast(agent._target_q_network.flat_params, 0)
+  spec = agent.collect_data_spec
+  rb = rb_mod.TFUniformReplayBuffer(spec, batch_size=B_ENV, max_length=L, device=dev,
+                                    seed=0x5eed0000 + rank)
+  g = torch.Generator(device=dev).manual_seed(1234 + rank)
+  st_store, obs_store, act_store, nst_store, rew_store, disc_store = rb._data_table.variables()
+  cap = B_ENV * L
+  chunk = 1 << 15
+  for i in range(0, cap, chunk):               # fill the ring in place (28 GB of random frames)
+    obs_store[i:i + chunk].view(-1).view(torch.int64).random_(generator=g)
+  st_store.copy_(torch.randint(0, 3, (cap,), device=dev, generator=g, dtype=torch.int32))
+  nst_store.copy_(torch.randint(0, 3, (cap,), device=dev, generator=g, dtype=torch.int32))
+  act_store.copy_(torch.randint(0, A, (cap,), device=dev, generator=g, dtype=torch.int32))
+  rew_store.copy_(torch.rand(cap, device=dev, generator=g))
+  disc_store.copy_((torch.rand(cap, device=dev, generator=g) > 0.1).float())
+  last_id = 2 * L + 77
+  pos = torch.arange(cap, device=dev, dtype=torch.int64) % L
+  rb._id_table.variables()[0].copy_(torch.where(pos <= last_id % L, last_id - last_id % L + pos,
+                                                last_id - last_id % L - L + pos))
+  rb._last_id.fill_(last_id)
+  rb._last_id_host = last_id
+
+  def step():
+    exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+    return agent.train(exp).loss
+
+  def sync_all():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize()
+
+  # launches of OUR kernels per step (counted on one eager step)
+  step()
+  torch.cuda.synchronize()
+  c0 = _lib.launch_count()
+  step()
+  torch.cuda.synchronize()
+  launches_per_step = _lib.launch_count() - c0
+
+  use_graph = not args.no_graph and world == 1
+  fn = common.function(step, warmup=1) if use_graph else step
+  for _ in range(W + 2):
+    fn()
+  sync_all()
+
+  # ---- timed region: K steps, CUDA events, max over ranks ---------------------------------------
+  clocks = ClockSampler(local_rank)
+  clocks.start()
+  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  sync_all()
+  e0.record()
+  for _ in range(K):
+    loss = fn()
+  e1.record()
+  sync_all()
+  ms = e0.elapsed_time(e1)
+  clk = clocks.stop()
+  if world > 1:
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+  final_loss = float(loss.item())
+  agent.check_numerics()
+  steps_per_s = K / (ms / 1000.0)
+  value = steps_per_s * world                  # batch-256-equivalent steps/s of the whole job
+
+  # ---- per-kernel timing for the rooflines (eager, CUDA events on the launch stream) ------------
+  n_g = 50
+  outs = []
+  for _ in range(5):
+    rb.get_next(sample_batch_size=B, num_steps=T)
+  torch.cuda.synchronize()
+  ge0, ge1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ge0.record()
+  for _ in range(n_g):
+    outs.append(rb.get_next(sample_batch_size=B, num_steps=T))   # distinct outputs, random rows
+  ge1.record()
+  torch.cuda.synchronize()
+  gather_ms = ge0.elapsed_time(ge1) / n_g
+  del outs
+  exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+  n_u = max(10, min(K, 50))
+  ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  agent.train(exp)
+  torch.cuda.synchronize()
+  ue0.record()
+  for _ in range(n_u):
+    agent.train(exp)
+  ue1.record()
+  torch.cuda.synchronize()
+  update_ms = ue0.elapsed_time(ue1) / n_u
+  traffic = {}
+  tp = os.path.join(ROOT, 'profiles', 'roofline_traffic.json')
+  if os.path.exists(tp):
+    traffic = json.load(open(tp))
+  gather_gbs = GATHER_BYTES / (gather_ms * 1e-3) / 1e9
+  update_tfs = FLOPS_PER_STEP / (update_ms * 1e-3) / 1e12
+
+  # ---- e2e: host buffers in, loss out, every step -----------------------------------------------
+  Ke = max(10, min(K, 100))
+  host = [torch.randint(0, 3, (B_ENV,), dtype=torch.int32).pin_memory(),
+          torch.randint(0, 256, (B_ENV, 84, 84, 4), dtype=torch.uint8).pin_memory(),
+          torch.randint(0, A, (B_ENV,), dtype=torch.int32).pin_memory(),
+          torch.randint(0, 3, (B_ENV,), dtype=torch.int32).pin_memory(),
+          torch.rand(B_ENV).pin_memory(), torch.ones(B_ENV).pin_memory()]
+  h2d = sum(t.numel() * t.element_size() for t in host)
+
+  def e2e_step():
+    items = trajectory.Trajectory(host[0].to(dev, non_blocking=True), host[1].to(dev, non_blocking=True),
+                                  host[2].to(dev, non_blocking=True), (),
+                                  host[3].to(dev, non_blocking=True), host[4].to(dev, non_blocking=True),
+                                  host[5].to(dev, non_blocking=True))
+    rb.add_batch(items)
+    exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+    return float(agent.train(exp).loss.item())          # device -> host read of the result
+
+  for _ in range(3):
+    e2e_step()
+  sync_all()
+  ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+  ee0.record()
+  for _ in range(Ke):
+    e2e_step()
+  ee1.record()
+  sync_all()
+  e2e_ms = ee0.elapsed_time(ee1)
+  if world > 1:
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item())
+  e2e_value = Ke / (e2e_ms / 1000.0) * world
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    sps, cores, sample = cpu_reference_steps(8, 1)
+    cpu = dict(value=sps, unit='steps/s', cores=cores, kind='port', sample=sample)
+
+  if rank == 0:
+    line = dict(
+        metric='train steps/sec (DQN Atari-shape, batch 256)', value=value, unit='steps/s',
+        n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
+        scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+        config=dict(workload='DQN synthetic Atari-shape obs 84x84x4 uint8, 1M-slot replay '
+                             f'({B_ENV}x{L}), batch {B}, T={T}, Mnih15 net, Huber, centered RMSProp',
+                    global_batch=B * world, per_gpu_batch=B, num_actions=A,
+                    parallelism=f'dp{world}' if world > 1 else 'single',
+                    l2='inputs > L2: 29.6 GB ring, fresh random rows every step',
+                    cuda_graph=bool(use_graph), collect_frames_per_e2e_step=B_ENV),
+        clocks=clk,
+        e2e=dict(value=e2e_value, unit='steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                 steps=Ke),
+        gpu_launches=int(launches_per_step * K),
+        roofline=dict(kernel='sgemm_kernel (Q-net conv/dense fwd+bwd, fp32 FFMA)', bound='tensor',
+                      achieved=update_tfs, peak=peaks['tensor'], unit='TFLOP/s',
+                      frac=update_tfs / peaks['tensor'], traffic=traffic.get('update'),
+                      peak_source=peaks['src'] + ' bf16 sustained', ms=update_ms,
+                      algorithmic_flops=FLOPS_PER_STEP),
+        roofline_gather=dict(kernel='row_copy_big<MODE_SAMPLE>', bound='hbm', achieved=gather_gbs,
+                             peak=peaks['hbm'], unit='GB/s', frac=gather_gbs / peaks['hbm'],
+                             traffic=traffic.get('gather'), peak_source=peaks['src'],
+                             us=gather_ms * 1e3, algorithmic_bytes=GATHER_BYTES),
+        final_loss=final_loss)
+    if cpu is not None:
+      line['cpu_baseline'] = cpu
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+  main()

@@ -1,0 +1,51 @@
+"""The C-ABI library loads and exports every symbol include/b200rl.h declares (no GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, 'include', 'b200rl.h')
+
+
+def _declared():
+  src = open(HEADER).read()
+  src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+  return sorted(set(re.findall(r'\b(b200rl_[a-z0-9_]+)\s*\(', src)))
+
+
+def test_header_declares_symbols():
+  names = _declared()
+  assert 'b200rl_rb_sample' in names and 'b200rl_dqn_td_loss' in names and len(names) >= 25
+
+
+def test_library_exports_every_declared_symbol():
+  from agents_b200 import _lib
+  if not os.path.exists(_lib.LIB_PATH):
+    import __graft_entry__
+    __graft_entry__.build()
+  l = ctypes.CDLL(_lib.LIB_PATH)
+  missing = [n for n in _declared() if not hasattr(l, n)]
+  assert not missing, missing
+
+
+def test_ctypes_signatures_cover_header():
+  from agents_b200 import _lib
+  bound = set(_lib.SIGNATURES) | set(_lib._RESTYPES)
+  assert set(_declared()) == bound
+
+
+def test_no_gpu_calls_fail_loudly_not_silently():
+  """Without CUDA tensors the product path raises instead of falling back to the CPU."""
+  import torch
+  from agents_b200 import _lib
+  with pytest.raises(_lib.B200RLError):
+    _lib.ptr(torch.zeros(4))
+
+
+def test_struct_layout_matches_header():
+  from agents_b200 import _lib
+  assert ctypes.sizeof(_lib.Leaf) == 16
+  assert ctypes.sizeof(_lib.Ring) == 8 + 8 + 8 + 8 + 8 + 8 + 16 * _lib.MAX_LEAVES
+  assert ctypes.sizeof(_lib.ConvGeom) == 40
