@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(256) eps_greedy_kernel(const float* __restrict
 
 // grid = (chunks, B).  Each thread fills 16 B of observation from one Philox block.
 __global__ void __launch_bounds__(256) env_random_step_kernel(
-    int32_t* __restrict__ step_type, void* __restrict__ obs, int64_t obs_elems, int obs_is_u8,
-    float* __restrict__ reward, float* __restrict__ discount, int64_t B, float p_term,
-    uint64_t seed, uint64_t* rng_call) {
+    int32_t* __restrict__ step_type, int32_t* __restrict__ out_step_type, void* __restrict__ obs,
+    int64_t obs_elems, int obs_is_u8, float* __restrict__ reward, float* __restrict__ discount,
+    int64_t B, float p_term, uint64_t seed, uint64_t* rng_call) {
   const int64_t b = blockIdx.y;
   const uint64_t call = rng_call[0];
   const int64_t vec_per_env = obs_is_u8 ? (obs_elems + 15) / 16 : (obs_elems + 3) / 4;
@@ -102,16 +102,19 @@ __global__ void __launch_bounds__(256) env_random_step_kernel(
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const Philox4 r = philox4x32_10(kStateDomain + (uint64_t)b, call, seed);
     const int32_t st = step_type[b];
+    int32_t nst;
     if (st == kLast) {  // auto-reset: ts.restart (time_step.py:135-195)
-      step_type[b] = kFirst;
+      nst = kFirst;
       reward[b] = 0.f;
       discount[b] = 1.f;
     } else {
       reward[b] = uniform_f32(r.x);
       const bool term = uniform_f32(r.y) < p_term;
-      step_type[b] = term ? kLast : kMid;  // ts.termination / ts.transition
+      nst = term ? kLast : kMid;  // ts.termination / ts.transition
       discount[b] = term ? 0.f : 1.f;
     }
+    step_type[b] = nst;
+    if (out_step_type) out_step_type[b] = nst;
   }
   bump_call(rng_call, (uint32_t*)(rng_call + 1));
 }
@@ -181,9 +184,10 @@ int b200rl_epsilon_greedy(const float* q, const int32_t* mask, int64_t B, int64_
   return B200RL_OK;
 }
 
-int b200rl_env_random_step(int32_t* step_type, void* obs, int64_t obs_elems, int obs_is_u8,
-                           float* reward, float* discount, int64_t B, float p_term,
-                           uint64_t seed, uint64_t* rng_call_dev, void* stream) {
+int b200rl_env_random_step(int32_t* step_type, int32_t* out_step_type, void* obs,
+                           int64_t obs_elems, int obs_is_u8, float* reward, float* discount,
+                           int64_t B, float p_term, uint64_t seed, uint64_t* rng_call_dev,
+                           void* stream) {
   B200RL_CHECK_ARG(step_type && obs && reward && discount && rng_call_dev && B >= 1 &&
                        obs_elems >= 1,
                    "env_random_step: bad argument");
@@ -191,7 +195,8 @@ int b200rl_env_random_step(int32_t* step_type, void* obs, int64_t obs_elems, int
   const int64_t vec = obs_is_u8 ? (obs_elems + 15) / 16 : (obs_elems + 3) / 4;
   dim3 grid((unsigned)((vec + 255) / 256), (unsigned)B);
   env_random_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      step_type, obs, obs_elems, obs_is_u8, reward, discount, B, p_term, seed, rng_call_dev);
+      step_type, out_step_type, obs, obs_elems, obs_is_u8, reward, discount, B, p_term, seed,
+      rng_call_dev);
   B200RL_CHECK_LAUNCH("env_random_step");
   return B200RL_OK;
 }

@@ -1,0 +1,33 @@
+"""Driver base (tf_agents/drivers/driver.py:26-85)."""
+import abc
+
+
+class Driver(abc.ABC):
+
+  def __init__(self, env, policy, observers=None, transition_observers=None,
+               info_observers=None):
+    self._env = env
+    self._policy = policy
+    self._observers = observers or []
+    self._transition_observers = transition_observers or []
+    self._info_observers = info_observers or []
+
+  @property
+  def env(self):
+    return self._env
+
+  @property
+  def policy(self):
+    return self._policy
+
+  @property
+  def observers(self):
+    return self._observers
+
+  @property
+  def transition_observers(self):
+    return self._transition_observers
+
+  @abc.abstractmethod
+  def run(self):
+    pass

@@ -244,10 +244,12 @@ int b200rl_epsilon_greedy(const float* q, const int32_t* mask, int64_t B, int64_
  *   if step_type[b]==LAST: -> FIRST, reward 0, discount 1, fresh obs
  *   else: reward~U[0,1), terminate w.p. p_term -> LAST/discount 0 else MID/discount 1.
  * obs is [B, obs_bytes] u8 (uniform 0..255) when obs_is_u8 else [B, obs_elems] f32 ~ N(0,1).
- * State (step_type) is read and written in place. */
-int b200rl_env_random_step(int32_t* step_type, void* obs, int64_t obs_elems, int obs_is_u8,
-                           float* reward, float* discount, int64_t B, float p_term,
-                           uint64_t seed, uint64_t* rng_call_dev, void* stream);
+ * State (step_type) is read and written in place; out_step_type (optional) receives a copy of
+ * the new step types so the caller can ping-pong its TimeStep output buffers. */
+int b200rl_env_random_step(int32_t* step_type, int32_t* out_step_type, void* obs,
+                           int64_t obs_elems, int obs_is_u8, float* reward, float* discount,
+                           int64_t B, float p_term, uint64_t seed, uint64_t* rng_call_dev,
+                           void* stream);
 
 /* Vectorised CartPole-v1 dynamics (gym classic_control formulae; the reference loads it via
  * suite_gym, agents/dqn/examples/v2/train_eval.py:151): state[B,4] f32, steps[B] int32. */

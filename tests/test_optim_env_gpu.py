@@ -114,7 +114,7 @@ def test_random_env_step_bit_exact(cuda, obs_elems, u8):
   wst = np.full(B, 2, np.int32)
   seen_last = False
   for call in range(12):
-    _lib.call('b200rl_env_random_step', _lib.ptr(st), _lib.ptr(obs), obs_elems, int(u8), _lib.ptr(rew),
+    _lib.call('b200rl_env_random_step', _lib.ptr(st), None, _lib.ptr(obs), obs_elems, int(u8), _lib.ptr(rew),
               _lib.ptr(disc), B, 0.3, 5, _lib.ptr(rngs), _lib.stream())
     wst, wobs, wrew, wdisc = oenv.random_env_step(wst, obs_elems, u8, 0.3, 5, call)
     np.testing.assert_array_equal(st.cpu().numpy(), wst)
