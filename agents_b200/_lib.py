@@ -51,6 +51,7 @@ class B200RLError(RuntimeError):
 # name -> argtypes (restype is int unless listed in _RESTYPES)
 _P = c_void_p
 SIGNATURES = {
+    'b200rl_set_copy_variant': [c_int],
     'b200rl_rb_add_batch': [ctypes.POINTER(Ring), _P, _P],
     'b200rl_rb_sample': [ctypes.POINTER(Ring), c_i64, c_i64, _P, _P, c_u64, _P, _P, _P, _P, _P,
                          _P, _P],

@@ -275,15 +275,30 @@ __global__ void act_bwd_kernel(const float* __restrict__ Y, const float* __restr
 
 // Column sums of dZ[M,N] in two deterministic stages.
 constexpr int kColRows = 512;  // rows per partial block
-__global__ void colsum_partial_kernel(const float* __restrict__ dZ, float* __restrict__ part,
-                                      int64_t M, int64_t N) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
+// Block = 32 columns x 8 row-lanes: a warp reads 128 contiguous bytes of one row, the 8 warps
+// walk kColRows rows in an interleaved fashion and are combined through shared memory in a
+// fixed order (deterministic).
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dZ,
+                                                             float* __restrict__ part, int64_t M,
+                                                             int64_t N) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t n = (int64_t)blockIdx.x * 32 + lane;
   const int64_t mb = (int64_t)blockIdx.y * kColRows;
   const int64_t me = mb + kColRows < M ? mb + kColRows : M;
   float s = 0.f;
-  for (int64_t m = mb; m < me; ++m) s += dZ[m * N + n];
-  part[(int64_t)blockIdx.y * N + n] = s;
+  if (n < N) {
+#pragma unroll 4
+    for (int64_t m = mb + w; m < me; m += 8) s += dZ[m * N + n];
+  }
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && n < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][lane];
+    part[(int64_t)blockIdx.y * N + n] = t;
+  }
 }
 __global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ db,
                                     int64_t nparts, int64_t N, int beta) {
@@ -391,8 +406,9 @@ static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, vo
   B200RL_CHECK_ARG(ws != nullptr && ws_bytes >= (int64_t)(nparts * N * sizeof(float)),
                    "bias gradient needs %lld bytes of workspace",
                    (long long)(nparts * N * sizeof(float)));
-  dim3 grid((unsigned)((N + 127) / 128), (unsigned)nparts);
-  colsum_partial_kernel<<<grid, 128, 0, st>>>(dZ, (float*)ws, M, N);
+  B200RL_CHECK_ARG(nparts <= 65535, "bias gradient: too many rows");
+  dim3 grid((unsigned)((N + 31) / 32), (unsigned)nparts);
+  colsum_partial_kernel<<<grid, 256, 0, st>>>(dZ, (float*)ws, M, N);
   B200RL_CHECK_LAUNCH("colsum_partial");
   colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)ws, db, nparts,
                                                                    N, beta);

@@ -8,6 +8,8 @@
 // (last_id / RNG call index) with a last-block-done ticket so the launch is CUDA-graph safe.
 //
 // HBM-bound byte movement: algorithmic bytes = 2 * rows * row_bytes (read ring + write batch).
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace b200rl {
@@ -229,6 +231,67 @@ __global__ void __launch_bounds__(kThreads) row_copy_big(const __grid_constant__
   finish<MODE>(p, last, ok);
 }
 
+// TMA variant of row_copy_big: one warp per (row, piece).  Lane 0 stages the piece through
+// shared memory with two bulk-async copies (global -> smem on an mbarrier, smem -> global as a
+// bulk group), so the whole transfer is issued by the copy engine in two instructions and
+// 16 CTAs x 14 KiB stay in flight per SM.  Lanes 1..31 carry the small leaves / ids.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(32) row_copy_tma(const __grid_constant__ Plan p) {
+  extern __shared__ __align__(128) unsigned char stage[];
+  __shared__ __align__(8) unsigned long long bar;
+  const int64_t blk = blockIdx.x;
+  const int64_t s = blk / p.pieces_per_row;
+  int piece = (int)(blk - s * p.pieces_per_row);
+  const int64_t last = p.last_id ? *p.last_id : 0;
+  int64_t src_row, dst_row, ring_row, new_id;
+  const bool ok = resolve_rows<MODE>(p, s, last, src_row, dst_row, ring_row, new_id);
+  if (ok) {
+    if (threadIdx.x == 0) {
+      int li = 0, pc = piece;
+      while (pc >= p.big[li].n_pieces) {
+        pc -= p.big[li].n_pieces;
+        ++li;
+      }
+      const PlanLeaf& lf = p.big[li];
+      const int64_t begin = (int64_t)pc * lf.piece_bytes;
+      int64_t len = lf.row_bytes - begin;
+      if (len > lf.piece_bytes) len = lf.piece_bytes;
+      const char* src = lf.src + src_row * lf.row_bytes + begin;
+      char* dst = lf.dst + dst_row * lf.row_bytes + begin;
+      const uint32_t bar_a = smem_u32(&bar), st_a = smem_u32(stage), n = (uint32_t)len;
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(n)
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+          ::"r"(st_a), "l"(src), "r"(n), "r"(bar_a)
+          : "memory");
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "WAIT_%=:\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
+          "@p bra DONE_%=;\n\t"
+          "bra WAIT_%=;\n\t"
+          "DONE_%=:\n\t}" ::"r"(bar_a)
+          : "memory");
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
+                   "r"(st_a), "r"(n)
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    } else if (piece == 0) {
+      small_and_meta<MODE>(p, s, src_row, dst_row, ring_row, new_id, last, threadIdx.x - 1, 31);
+    }
+  }
+  finish<MODE>(p, last, ok);
+}
+
 // All-small rows (MuJoCo-shape: 108-160 B): one warp per row, 8 rows per CTA.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) row_copy_small(const __grid_constant__ Plan p) {
@@ -272,6 +335,17 @@ __global__ void draw_kernel(const __grid_constant__ Plan p) {
 }
 
 __global__ void clear_kernel(int64_t* last_id) { *last_id = -1; }
+
+// 0 = LDG/STG kernel (row_copy_big), 1 = TMA bulk-copy kernel (row_copy_tma).
+// B200RL_COPY_VARIANT overrides the default (used by profiles/gather_sweep.py for A/B runs).
+static int g_copy_variant = -1;
+static int copy_variant() {
+  if (g_copy_variant < 0) {
+    const char* e = getenv("B200RL_COPY_VARIANT");
+    g_copy_variant = e ? atoi(e) : 1;
+  }
+  return g_copy_variant;
+}
 
 static int widest_vec(int64_t row_bytes, const void* a, const void* b) {
   uintptr_t bits = (uintptr_t)row_bytes | (uintptr_t)a | (uintptr_t)b;
@@ -330,7 +404,17 @@ static int launch_plan(Plan& p, cudaStream_t st, const char* name) {
   if (p.n_big > 0) {
     int64_t grid = p.n_rows * p.pieces_per_row;
     B200RL_CHECK_ARG(grid < (1ll << 31), "%s: grid too large", name);
-    row_copy_big<MODE><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    bool tma_ok = copy_variant() == 1;
+    int max_piece = 0;
+    for (int i = 0; i < p.n_big; ++i) {
+      if (p.big[i].vec != 16) tma_ok = false;
+      if (p.big[i].piece_bytes > max_piece) max_piece = p.big[i].piece_bytes;
+    }
+    if (tma_ok) {
+      row_copy_tma<MODE><<<(unsigned)grid, 32, max_piece, st>>>(p);
+    } else {
+      row_copy_big<MODE><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    }
   } else {
     int64_t grid = (p.n_rows + p.rows_per_cta - 1) / p.rows_per_cta;
     B200RL_CHECK_ARG(grid < (1ll << 31), "%s: grid too large", name);
@@ -345,6 +429,12 @@ static int launch_plan(Plan& p, cudaStream_t st, const char* name) {
 using namespace b200rl;
 
 extern "C" {
+
+int b200rl_set_copy_variant(int v) {
+  B200RL_CHECK_ARG(v == 0 || v == 1, "copy variant must be 0 (LDG) or 1 (TMA bulk)");
+  g_copy_variant = v;
+  return B200RL_OK;
+}
 
 int b200rl_rb_add_batch(const b200rl_ring_t* ring, const void* const* items, void* stream) {
   Plan p;

@@ -76,6 +76,11 @@ typedef struct {
   b200rl_leaf_t leaves[B200RL_MAX_LEAVES];
 } b200rl_ring_t;
 
+/* Selects the row-copy kernel used by every ring read/write: 0 = 16-byte LDG/STG kernel,
+ * 1 = TMA bulk-copy (cp.async.bulk) kernel.  Default: env B200RL_COPY_VARIANT, else 1 (TMA:
+ * 5.7 TB/s vs 3.6 TB/s at batch 4096, profiles/r1_gather_sweep.jsonl). */
+int b200rl_set_copy_variant(int variant);
+
 /* _add_batch (tf_uniform_replay_buffer.py:182-209): id = ++last_id; rows[b] = b*L + id % L;
  * scatter every leaf row and the id.  items[i] is a device pointer to [B_env, row_bytes_i]. */
 int b200rl_rb_add_batch(const b200rl_ring_t* ring, const void* const* items, void* stream);
