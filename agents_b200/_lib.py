@@ -62,6 +62,19 @@ SIGNATURES = {
     'b200rl_rb_draw': [ctypes.POINTER(Ring), c_i64, c_i64, c_u64, _P, _P, _P, _P],
     'b200rl_discounted_return': [_P, _P, _P, _P, c_i64, c_i64, c_int, c_int, _P],
     'b200rl_gae': [_P, _P, _P, _P, c_f32, _P, c_i64, c_i64, c_int, _P],
+    'b200rl_discounted_return_ld': [_P, _P, _P, _P, c_i64, c_i64, c_i64, c_i64, c_i64, _P],
+    'b200rl_gae_ld': [_P, _P, _P, _P, c_f32, _P, c_i64, c_i64, c_i64, c_i64, c_i64, _P],
+    'b200rl_ppo_loss': [_P, _P, c_i64, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_f32, c_f32,
+                        c_f32, c_f32, c_f32, c_f32, _P, _P, _P, c_i64, _P, _P, _P, c_i64, _P],
+    'b200rl_normal_logp': [_P, _P, c_i64, _P, c_i64, c_i64, _P, _P],
+    'b200rl_normal_sample': [_P, _P, c_i64, c_i64, c_i64, _P, _P, c_u64, _P, _P, _P],
+    'b200rl_normal_proj_fwd': [_P, _P, _P, _P, c_i64, c_i64, _P, _P, _P],
+    'b200rl_normal_proj_bwd': [_P, _P, _P, _P, _P, _P, c_i64, c_i64, _P, _P, _P],
+    'b200rl_colsum': [_P, _P, c_int, c_i64, c_i64, c_f32, _P, _P, c_i64, _P],
+    'b200rl_normalize': [_P, _P, c_i64, c_i64, _P, _P, _P, c_f32, c_f32, _P],
+    'b200rl_normalizer_update': [_P, _P, _P, _P, _P, _P, c_f32, c_i64, _P],
+    'b200rl_ppo_discounts': [_P, _P, c_f32, c_i64, _P, _P],
+    'b200rl_ppo_weights': [_P, _P, _P, _P, c_i64, _P, _P],
     'b200rl_nstep_reduce': [_P, _P, c_f64, _P, _P, c_i64, c_i64, _P],
     'b200rl_dqn_td_loss': [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_f64, c_f64,
                            c_int, c_f32, _P, _P, _P, _P, _P, _P],

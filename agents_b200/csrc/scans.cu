@@ -41,14 +41,16 @@ __global__ void __launch_bounds__(256) scan_batch_major(const float* __restrict_
                                                         const float* __restrict__ values,
                                                         const float* __restrict__ final_value,
                                                         float td_lambda, float* __restrict__ out,
-                                                        int64_t B, int64_t T, int provide_all) {
+                                                        int64_t B, int64_t T, int provide_all,
+                                                        int64_t ld_in, int64_t ld_out,
+                                                        int64_t fv_stride) {
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
-  const float* r = rewards + b * T;
-  const float* d = discounts + b * T;
-  const float* v = KIND == 1 ? values + b * T : nullptr;
-  const float fin = final_value ? final_value[b] : 0.f;
+  const float* r = rewards + b * ld_in;
+  const float* d = discounts + b * ld_in;
+  const float* v = KIND == 1 ? values + b * ld_in : nullptr;
+  const float fin = final_value ? final_value[b * fv_stride] : 0.f;
   float carry = KIND == 1 ? 0.f : fin;
   const int64_t ntiles = (T + 31) / 32;
   for (int64_t tile = ntiles - 1; tile >= 0; --tile) {
@@ -69,7 +71,7 @@ __global__ void __launch_bounds__(256) scan_batch_major(const float* __restrict_
     m = warp_suffix_compose(m, lane);
     const float y = __fadd_rn(__fmul_rn(m.a, carry), m.b);
     if (t < T && (provide_all || t == 0)) {
-      if (provide_all) out[b * T + t] = y;
+      if (provide_all) out[b * ld_out + t] = y;
       else out[b] = y;
     }
     carry = __shfl_sync(0xffffffffu, y, 0);
@@ -138,7 +140,7 @@ int b200rl_discounted_return(const float* rewards, const float* discounts,
         rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all);
   } else {
     scan_batch_major<0><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(
-        rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all);
+        rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all, T, T, 1);
   }
   B200RL_CHECK_LAUNCH("discounted_return");
   return B200RL_OK;
@@ -157,9 +159,35 @@ int b200rl_gae(const float* values, const float* final_value, const float* disco
         rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1);
   } else {
     scan_batch_major<1><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(
-        rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1);
+        rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, T, T, 1);
   }
   B200RL_CHECK_LAUNCH("gae");
+  return B200RL_OK;
+}
+
+/* Batch-major scans over the first T columns of [B, ld] arrays (ld >= T): used by PPO, whose
+ * returns/advantages cover T-1 of the T collected steps (ppo_agent.py:617-719); out rows have
+ * stride ld_out, final_value[b] is read at final_value[b * fv_stride]. */
+int b200rl_discounted_return_ld(const float* rewards, const float* discounts,
+                                const float* final_value, float* out, int64_t B, int64_t T,
+                                int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream) {
+  B200RL_CHECK_ARG(rewards && discounts && out, "discounted_return_ld: NULL argument");
+  B200RL_CHECK_ARG(B >= 1 && T >= 1 && ld_in >= T && ld_out >= T, "discounted_return_ld: sizes");
+  scan_batch_major<0><<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      rewards, discounts, nullptr, final_value, 0.f, out, B, T, 1, ld_in, ld_out, fv_stride);
+  B200RL_CHECK_LAUNCH("discounted_return_ld");
+  return B200RL_OK;
+}
+
+int b200rl_gae_ld(const float* values, const float* final_value, const float* discounts,
+                  const float* rewards, float td_lambda, float* out_adv, int64_t B, int64_t T,
+                  int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream) {
+  B200RL_CHECK_ARG(values && final_value && discounts && rewards && out_adv, "gae_ld: NULL");
+  B200RL_CHECK_ARG(B >= 1 && T >= 1 && ld_in >= T && ld_out >= T, "gae_ld: sizes");
+  scan_batch_major<1><<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, ld_in, ld_out,
+      fv_stride);
+  B200RL_CHECK_LAUNCH("gae_ld");
   return B200RL_OK;
 }
 

@@ -206,3 +206,40 @@ class Network(object):
       l, x, y = tape[i]
       dy = l.backward(x, y, dy, need_dx=i > first)
     return self._grads
+
+
+def allocate_jointly(networks):
+  """Re-homes the parameters of several built Networks into ONE flat buffer (and one gradient
+  buffer) so a single optimiser / clip / all-reduce launch covers all of them — the reference
+  applies one optimizer to `actor_net.trainable_weights + value_net.trainable_weights`
+  (agents/ppo/ppo_agent.py:916-923).  Returns (flat_params, flat_grads)."""
+  for n in networks:
+    n._require_built()
+  total = sum(n._params.numel() for n in networks)
+  dev = networks[0].device
+  params = torch.zeros(total, dtype=torch.float32, device=dev)
+  grads = torch.zeros_like(params)
+  off = 0
+  for n in networks:
+    k = n._params.numel()
+    params[off:off + k].copy_(n._params)
+    n._params = params[off:off + k]
+    n._grads = grads[off:off + k]
+    n._param_views, n._grad_views = [], []
+    i = 0
+    for l in n._layers:
+      shapes = l.param_shapes()
+      if not shapes:
+        continue
+      pv, gv = [], []
+      for ps in shapes:
+        cnt = int(np.prod(ps))
+        o = n._offsets[i]
+        pv.append(n._params[o:o + cnt].view(ps))
+        gv.append(n._grads[o:o + cnt].view(ps))
+        i += 1
+      l.bind(pv, gv)
+      n._param_views.extend(pv)
+      n._grad_views.extend(gv)
+    off += k
+  return params, grads

@@ -132,6 +132,14 @@ int b200rl_gae(const float* values, const float* final_value, const float* disco
                const float* rewards, float td_lambda, float* out_adv, int64_t B, int64_t T,
                int time_major, void* stream);
 
+/* Batch-major variants over the first T columns of [B, ld] arrays (PPO: T-1 of T steps). */
+int b200rl_discounted_return_ld(const float* rewards, const float* discounts,
+                                const float* final_value, float* out, int64_t B, int64_t T,
+                                int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream);
+int b200rl_gae_ld(const float* values, const float* final_value, const float* discounts,
+                  const float* rewards, float td_lambda, float* out_adv, int64_t B, int64_t T,
+                  int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream);
+
 /* to_n_step_transition reward/discount reduction (trajectories/trajectory.py:815-832):
  * reward,discount are [B,T] (T = n+1, last column ignored). */
 int b200rl_nstep_reduce(const float* reward, const float* discount, double gamma,
@@ -160,6 +168,60 @@ int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt, const float* nex
                        int64_t T, double gamma, double reward_scale, int loss_kind,
                        float global_batch, float* loss, float* td_loss, float* td_error,
                        float* dq, int32_t* nan_flag, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * PPO update math — agents/ppo/ppo_agent.py, ppo_utils.py, utils/tensor_normalizer.py
+ * ------------------------------------------------------------------------------------ */
+/* Fused clipped-surrogate / value / entropy losses + gradients over N = B*T elements
+ * (ppo_agent.py:1159-1201 entropy, :1203-1327 value, :1329-1512 policy gradient; each is
+ * sum(loss*w) / (T * global_batch), utils/common.py:1400-1476).  The current policy is a diagonal
+ * Normal(loc, scale) given as [N, A] views with row stride ld_ls; gradients are written with row
+ * stride ld_g.  clip_eps <= 0, value_clip <= 0, logp_clip <= 0 disable the respective clipping.
+ * losses[5] = {policy_gradient, value_estimation (x vf_coef), entropy_regularization (x ent_coef),
+ * clip_fraction, sum of the three losses}. */
+int b200rl_ppo_loss(const float* loc, const float* scale, int64_t ld_ls, const float* action,
+                    const float* old_logp, const float* adv, const float* ret, const float* v,
+                    const float* v_old, const float* w, int64_t N, int64_t A, int64_t T,
+                    float global_batch, float clip_eps, float value_clip, float vf_coef,
+                    float ent_coef, float logp_clip, float* losses, float* dloc, float* dscale,
+                    int64_t ld_g, float* dv, int32_t* nan_flag, void* workspace,
+                    int64_t ws_bytes, void* stream);
+/* log-prob of actions under Normal(loc, scale), summed over action dims (common.py:682-717). */
+int b200rl_normal_logp(const float* loc, const float* scale, int64_t ld, const float* action,
+                       int64_t N, int64_t A, float* out, void* stream);
+/* action = clip(loc + scale * z, amin, amax), z ~ N(0,1) (Philox + Box-Muller);
+ * rng_call_dev is uint64[2] {call, ticket}. */
+int b200rl_normal_sample(const float* loc, const float* scale, int64_t ld, int64_t N, int64_t A,
+                         const float* amin, const float* amax, uint64_t seed,
+                         uint64_t* rng_call_dev, float* out, void* stream);
+/* NormalProjectionNetwork head (networks/normal_projection_network.py): loc = tanh-squash of the
+ * mean layer to [amin, amax], scale = softplus(bias) broadcast; bwd returns dm_raw and the
+ * per-element d(scale bias) terms (column-sum them with b200rl_colsum). */
+int b200rl_normal_proj_fwd(const float* m_raw, const float* s_raw, const float* amin,
+                           const float* amax, int64_t N, int64_t A, float* loc, float* scale,
+                           void* stream);
+int b200rl_normal_proj_bwd(const float* m_raw, const float* s_raw, const float* amin,
+                           const float* amax, const float* dloc, const float* dscale, int64_t N,
+                           int64_t A, float* dm_raw, float* ds_part, void* stream);
+/* out[c] = scale * sum_r f(x[r,c]), f = identity or (x - center[c])^2 — the two passes of
+ * tf.nn.moments (ppo_agent.py:100-110) and of the streaming normaliser. Deterministic. */
+int b200rl_colsum(const float* x, const float* center, int squared, int64_t rows, int64_t cols,
+                  float scale, float* out, void* workspace, int64_t ws_bytes, void* stream);
+/* tf.nn.batch_normalization without offset/scale: out = x*inv - mean*inv, inv = rsqrt(var+eps),
+ * var = m2/count (count NULL: m2 is the variance); mean NULL -> 0; clip > 0 clips to +-clip
+ * (utils/tensor_normalizer.py:134-205). */
+int b200rl_normalize(const float* x, float* out, int64_t rows, int64_t cols, const float* mean,
+                     const float* m2, const float* count, float eps, float clip, void* stream);
+/* StreamingTensorNormalizer update: Chan merge + Kahan carry (tensor_normalizer.py:397-470). */
+int b200rl_normalizer_update(float* count, float* avg, float* m2, float* carry,
+                             const float* avg_a, const float* m2_a, float n_a, int64_t cols,
+                             void* stream);
+/* gamma * discount * (next_step_type != LAST) (ppo_agent.py:632-660). */
+int b200rl_ppo_discounts(const float* discount, const int32_t* next_step_type, float gamma,
+                         int64_t n, float* out, void* stream);
+/* make_trajectory_mask (ppo_utils.py:35-59) times optional weights. */
+int b200rl_ppo_weights(const int32_t* step_type, const float* ret, const float* adv,
+                       const float* weights, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Network layers (fp32).  Replace Keras Dense/Conv2D fwd+bwd that the reference executes
