@@ -454,7 +454,7 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
 int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
                      float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
                      void* workspace, int64_t ws_bytes, void* stream) {
-  B200RL_CHECK_ARG(X && W && dY && dW, "dense_bwd: NULL argument");
+  B200RL_CHECK_ARG(X && W && dY, "dense_bwd: NULL argument");
   B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_bwd: ldx < K");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
@@ -463,7 +463,7 @@ int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* d
     rc = launch_gemm(ARow{dY, N}, BCol{W, N}, g);
     if (rc) return rc;
   }
-  {
+  if (dW) {
     GemmArgs g{dW, nullptr, K, N, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
     rc = launch_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g);
     if (rc) return rc;

@@ -158,7 +158,7 @@ class Dense(Layer):
               self.units, self._act, _lib.ptr(ws), nb, _lib.stream())
     return y
 
-  def backward(self, x, y, dy, need_dx):
+  def backward(self, x, y, dy, need_dx, need_dw=True):
     x, ldx = _batch_strided(x, self.in_features)
     m = x.shape[0]
     dy = dy.contiguous()
@@ -171,7 +171,8 @@ class Dense(Layer):
     dx = torch.empty((m, self.in_features), dtype=torch.float32, device=x.device) if need_dx else None
     ws, nb = workspace.get(x.device)
     _lib.call('b200rl_dense_bwd', _lib.dptr(x), ldx, _lib.ptr(self.kernel), _lib.ptr(dz),
-              _lib.ptr(dx), _lib.ptr(self.d_kernel), _lib.ptr(self.d_bias), m, self.in_features,
+              _lib.ptr(dx), _lib.ptr(self.d_kernel) if need_dw else None,
+              _lib.ptr(self.d_bias) if need_dw else None, m, self.in_features,
               self.units, 0, _lib.ptr(ws), nb, _lib.stream())
     return dx
 

@@ -199,12 +199,22 @@ class Network(object):
     """Forward that records activations; returns (output, tape)."""
     return self._run(observation, keep=True)
 
-  def backward(self, tape, dy):
-    """Back-propagates dLoss/d(output) through `tape`, OVERWRITING flat_grads."""
+  def backward(self, tape, dy, need_input_grad=False, need_param_grads=True):
+    """Back-propagates dLoss/d(output) through `tape`, OVERWRITING flat_grads.
+
+    need_input_grad: also return dLoss/d(input) (SAC's actor loss differentiates the critics
+    w.r.t. their action input); need_param_grads=False skips the weight gradients (dense only).
+    Returns flat_grads, or (flat_grads, d_input) when need_input_grad."""
     first = next(i for i, (l, _, _) in enumerate(tape) if l.has_params)
     for i in range(len(tape) - 1, -1, -1):
       l, x, y = tape[i]
-      dy = l.backward(x, y, dy, need_dx=i > first)
+      need_dx = need_input_grad or i > first
+      if not need_param_grads and isinstance(l, layers_lib.Dense):
+        dy = l.backward(x, y, dy, need_dx=need_dx, need_dw=False)
+      else:
+        dy = l.backward(x, y, dy, need_dx=need_dx)
+    if need_input_grad:
+      return self._grads, dy
     return self._grads
 
 

@@ -224,6 +224,46 @@ int b200rl_ppo_weights(const int32_t* step_type, const float* ret, const float* 
                        const float* weights, int64_t n, float* out, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * SAC update math — agents/sac/sac_agent.py, sac/tanh_normal_projection_network.py,
+ * distributions/utils.py (SquashToSpecNormal), distributions/tanh_bijector_stable.py
+ * ------------------------------------------------------------------------------------ */
+/* _actions_and_log_probs (sac_agent.py:537-557) for the tanh-Normal policy: head [N, 2A] =
+ * (loc | log_std); u = loc + exp(log_std)*eps, action = tanh-squash of u to [amin, amax] (written
+ * with row stride ld_action), logp = log pi(action).  eps_in (oracle mode) or Philox+Box-Muller
+ * (rng_call_dev uint64[2]).  u_out / eps_out (optional) are saved for the backward. */
+int b200rl_sac_sample(const float* head, int64_t N, int64_t A, const float* amin,
+                      const float* amax, const float* eps_in, uint64_t seed,
+                      uint64_t* rng_call_dev, float* action, int64_t ld_action, float* logp,
+                      float* u_out, float* eps_out, void* stream);
+/* dL/dhead from dL/daction (da1 + da2, [N, ld_da] views, either may be NULL) and dL/dlogp. */
+int b200rl_sac_sample_bwd(const float* head, const float* u_saved, const float* eps_saved,
+                          const float* amin, const float* amax, const float* da1,
+                          const float* da2, int64_t ld_da, const float* dlogp, int64_t N,
+                          int64_t A, float* dhead, void* stream);
+/* critic_loss (sac_agent.py:559-643) with squared TD error: y = rs*r + gamma*d*(min(tq1,tq2) -
+ * exp(log_alpha)*next_logp); loss = loss_weight * sum(w*((y-q1)^2 + (y-q2)^2)) / global_batch. */
+int b200rl_sac_critic_loss(const float* q1, const float* q2, const float* tq1, const float* tq2,
+                           const float* next_logp, const float* reward, const float* discount,
+                           const float* weights, const float* log_alpha_dev, int64_t B,
+                           float gamma, float reward_scale, float loss_weight,
+                           float global_batch, float* loss, float* dq1, float* dq2,
+                           float* td_targets, int32_t* nan_flag, void* stream);
+/* actor_loss (sac_agent.py:645-694): sum(w*(exp(log_alpha)*logp - min(q1,q2))) / global_batch. */
+int b200rl_sac_actor_loss(const float* q1, const float* q2, const float* logp,
+                          const float* weights, const float* log_alpha_dev, int64_t B,
+                          float loss_weight, float global_batch, float* loss, float* dlogp,
+                          float* dq1, float* dq2, int32_t* nan_flag, void* stream);
+/* alpha_loss (sac_agent.py:696-739). */
+int b200rl_sac_alpha_loss(const float* logp, const float* weights, const float* log_alpha_dev,
+                          int64_t B, float target_entropy, int use_log_alpha, float loss_weight,
+                          float global_batch, float* loss, float* dlog_alpha, int32_t* nan_flag,
+                          void* stream);
+/* out[N, da+db] = (a[N, :da] | b[N, :db]) — the critic's concat(observation, action) input
+ * (agents/ddpg/critic_network.py:163-178). */
+int b200rl_concat2(const float* a, int64_t lda, int64_t da, const float* b, int64_t ldb,
+                   int64_t db, int64_t N, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------
  * Network layers (fp32).  Replace Keras Dense/Conv2D fwd+bwd that the reference executes
  * through TensorFlow (networks/encoding_network.py:224-312, q_network.py:126-135).
  * All matrices are row-major.
@@ -235,7 +275,8 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
                      int64_t M, int64_t K, int64_t N, int act, void* workspace,
                      int64_t ws_bytes, void* stream);
 /* Given dY[M,N] (already multiplied by act'), compute dX[M,K] (optional, NULL to skip),
- * dW[K,N] and db[N].  accumulate!=0 adds into dW/db instead of overwriting. */
+ * dW[K,N] (optional) and db[N] (optional).  accumulate!=0 adds into dW/db instead of
+ * overwriting. */
 int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
                      float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
                      void* workspace, int64_t ws_bytes, void* stream);
