@@ -70,7 +70,8 @@ def test_clip_kernels(cuda):
   offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
   g = (rng.randn(offs[-1]) * 3).astype(f32)
   tg = torch.as_tensor(g.copy(), device=cuda)
-  _lib.call('b200rl_clip_by_norm_segments', _lib.ptr(tg), _lib.ptr(torch.as_tensor(offs, device=cuda)),
+  toffs = torch.as_tensor(offs, device=cuda)
+  _lib.call('b200rl_clip_by_norm_segments', _lib.ptr(tg), _lib.ptr(toffs),
             len(sizes), 2.0, _lib.stream())
   want = np.concatenate([ooptim.clip_by_norm(g[offs[i]:offs[i + 1]], 2.0) for i in range(len(sizes))])
   np.testing.assert_allclose(tg.cpu().numpy(), want, rtol=1e-5, atol=1e-7)
@@ -135,8 +136,9 @@ def test_cartpole_step_parity(cuda):
   wstate, wsteps, wst = np.zeros((B, 4), f32), np.zeros(B, np.int32), np.full(B, 2, np.int32)
   for call in range(60):
     act = rng.randint(0, 2, size=B).astype(np.int32)
+    tact = torch.as_tensor(act, device=cuda)
     _lib.call('b200rl_env_cartpole_step', _lib.ptr(state), _lib.ptr(steps), _lib.ptr(st),
-              _lib.ptr(torch.as_tensor(act, device=cuda)), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(disc), B, 25,
+              _lib.ptr(tact), _lib.ptr(obs), _lib.ptr(rew), _lib.ptr(disc), B, 25,
               11, _lib.ptr(rngs), _lib.stream())
     # step the oracle from the device state so 1-ulp sin/cos differences cannot accumulate
     wstate, wsteps, wst2, wobs, wrew, wdisc = oenv.cartpole_step(wstate, wsteps, wst, act, 25, 11, call)

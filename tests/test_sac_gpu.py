@@ -30,22 +30,23 @@ def test_reference_goldens_through_kernels(cuda):
   # :375-396 (alpha -52) with log_pi mocked to 10
   la = torch.zeros(4, device=cuda)
   q, tq = _d(cuda, [7., 10.]), _d(cuda, [7., 9.])
+  logpi, rew, disc = _d(cuda, [10., 10.]), _d(cuda, [10., 20.]), _d(cuda, [.9, .9])   # keep alive
   loss = torch.empty(1, device=cuda); dq1 = torch.empty(2, device=cuda); dq2 = torch.empty(2, device=cuda)
   y = torch.empty(2, device=cuda)
   _lib.call('b200rl_sac_critic_loss', _lib.ptr(q), _lib.ptr(q), _lib.ptr(tq), _lib.ptr(tq),
-            _lib.ptr(_d(cuda, [10., 10.])), _lib.ptr(_d(cuda, [10., 20.])), _lib.ptr(_d(cuda, [.9, .9])), None,
+            _lib.ptr(logpi), _lib.ptr(rew), _lib.ptr(disc), None,
             _lib.ptr(la), 2, 1.0, 1.0, 1.0, 2.0, _lib.ptr(loss), _lib.ptr(dq1), _lib.ptr(dq2), _lib.ptr(y), None,
             _lib.stream())
   np.testing.assert_allclose(y.cpu().numpy(), [7.3, 19.1], rtol=1e-6)
   np.testing.assert_allclose(loss.item(), 2 * np.mean((np.array([7.3, 19.1]) - [7., 10.]) ** 2), rtol=1e-6)
   qa = _d(cuda, [3., 5.])
   dl = torch.empty(2, device=cuda)
-  _lib.call('b200rl_sac_actor_loss', _lib.ptr(qa), _lib.ptr(qa), _lib.ptr(_d(cuda, [10., 10.])), None, _lib.ptr(la), 2,
+  _lib.call('b200rl_sac_actor_loss', _lib.ptr(qa), _lib.ptr(qa), _lib.ptr(logpi), None, _lib.ptr(la), 2,
             1.0, 2.0, _lib.ptr(loss), _lib.ptr(dl), _lib.ptr(dq1), _lib.ptr(dq2), None, _lib.stream())
   np.testing.assert_allclose(loss.item(), 6.0, rtol=1e-6)
   la[0] = 4.0
   dla = torch.empty(4, device=cuda)
-  _lib.call('b200rl_sac_alpha_loss', _lib.ptr(_d(cuda, [10., 10.])), None, _lib.ptr(la), 2, 3.0, 1, 1.0, 2.0,
+  _lib.call('b200rl_sac_alpha_loss', _lib.ptr(logpi), None, _lib.ptr(la), 2, 3.0, 1, 1.0, 2.0,
             _lib.ptr(loss), _lib.ptr(dla), None, _lib.stream())
   np.testing.assert_allclose(loss.item(), -52.0, rtol=1e-6)
   np.testing.assert_allclose(dla[0].item(), -13.0, rtol=1e-6)
@@ -60,14 +61,15 @@ def test_sample_and_logp_parity(cuda):
   wa, wl, wu = osac.sample_and_log_prob(head, eps, amin, amax)
   act = torch.empty(N, A, device=cuda); logp = torch.empty(N, device=cuda)
   u = torch.empty(N, A, device=cuda); e = torch.empty(N, A, device=cuda)
-  _lib.call('b200rl_sac_sample', _lib.ptr(_d(cuda, head)), N, A, _lib.ptr(_d(cuda, amin)), _lib.ptr(_d(cuda, amax)),
-            _lib.ptr(_d(cuda, eps)), 0, None, _lib.ptr(act), A, _lib.ptr(logp), _lib.ptr(u), _lib.ptr(e), _lib.stream())
+  th, tmin, tmax, teps = _d(cuda, head), _d(cuda, amin), _d(cuda, amax), _d(cuda, eps)   # keep alive
+  _lib.call('b200rl_sac_sample', _lib.ptr(th), N, A, _lib.ptr(tmin), _lib.ptr(tmax),
+            _lib.ptr(teps), 0, None, _lib.ptr(act), A, _lib.ptr(logp), _lib.ptr(u), _lib.ptr(e), _lib.stream())
   np.testing.assert_allclose(act.cpu().numpy(), wa, rtol=1e-5, atol=1e-6)
   np.testing.assert_allclose(logp.cpu().numpy(), wl, rtol=1e-5, atol=1e-4)
   np.testing.assert_allclose(u.cpu().numpy(), wu, rtol=1e-6, atol=1e-6)
   # device-drawn noise is N(0,1) and advances the call counter
   rngs = torch.zeros(2, dtype=torch.int64, device=cuda)
-  _lib.call('b200rl_sac_sample', _lib.ptr(_d(cuda, head)), N, A, _lib.ptr(_d(cuda, amin)), _lib.ptr(_d(cuda, amax)),
+  _lib.call('b200rl_sac_sample', _lib.ptr(th), N, A, _lib.ptr(tmin), _lib.ptr(tmax),
             None, 7, _lib.ptr(rngs), _lib.ptr(act), A, _lib.ptr(logp), _lib.ptr(u), _lib.ptr(e), _lib.stream())
   z = e.cpu().numpy()
   assert abs(z.mean()) < 0.05 and abs(z.std() - 1) < 0.05 and rngs.cpu().tolist() == [1, 0]
