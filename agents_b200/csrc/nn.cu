@@ -16,6 +16,7 @@
 // go to the caller's workspace and a second kernel reduces them in fixed order and applies
 // bias + activation, so results are run-to-run bit-stable.
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -128,6 +129,10 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == B200RL_ACT_TANH) return tanhf(v);
   return v;
 }
+
+}  // namespace b200rl
+#include "tc_gemm.cuh"
+namespace b200rl {
 
 constexpr int BK = 16;
 
@@ -385,11 +390,77 @@ static int launch_gemm_cfg(const AL& a, const BL& b, const GemmArgs& g) {
   return B200RL_OK;
 }
 
+// 0 = fp32 FFMA (sgemm_kernel), 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 (not 1e-5 safe)
+static int g_gemm_mode = -1;
+static int gemm_mode() {
+  if (g_gemm_mode < 0) {
+    const char* e = getenv("B200RL_GEMM_MODE");
+    g_gemm_mode = e ? atoi(e) : 0;
+  }
+  return g_gemm_mode;
+}
+
+template <int BN, int STAGES, int PASSES, class AL, class BL>
+static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
+  using L = tc::SmemLayout<BN, STAGES, PASSES>;
+  auto kernel = tc::tc_gemm_kernel<BN, STAGES, PASSES, AL, BL>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kBytes);
+    if (e != cudaSuccess) {
+      set_error("tc_gemm: cannot set dynamic smem to %d: %s", L::kBytes, cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t tm = (g.M + tc::kBM - 1) / tc::kBM, tn = (g.N + BN - 1) / BN;
+  const int64_t tiles = tm * tn;
+  int splits = 1;
+  if (tiles < kNumSMs && g.K >= 8 * tc::kBK && g.ws != nullptr) {
+    int64_t want = (kNumSMs + tiles - 1) / tiles;
+    int64_t max_by_k = g.K / (4 * tc::kBK);
+    int64_t max_by_ws = g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t s = want < max_by_k ? want : max_by_k;
+    if (s > max_by_ws) s = max_by_ws;
+    if (s > 65535) s = 65535;
+    if (s >= 2) splits = (int)s;
+  }
+  int64_t kps = (g.K + splits - 1) / splits;
+  kps = (kps + tc::kBK - 1) / tc::kBK * tc::kBK;
+  splits = (int)((g.K + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  B200RL_CHECK_ARG(tm <= 65535, "tc_gemm: M too large for grid.y (%lld tiles)", (long long)tm);
+  dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
+  kernel<<<grid, tc::kThreads, L::kBytes, g.st>>>(a, b, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta,
+                                                  splits, kps, (float*)g.ws);
+  B200RL_CHECK_LAUNCH("tc_gemm");
+  if (splits > 1) {
+    const int64_t MN = g.M * g.N;
+    splitk_reduce_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, g.st>>>(
+        (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta);
+    B200RL_CHECK_LAUNCH("splitk_reduce");
+  }
+  return B200RL_OK;
+}
+
+template <int PASSES, class AL, class BL>
+static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
+  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES>(a, b, g);
+  if (g.N <= 64) return launch_tc_cfg<64, 4, PASSES>(a, b, g);
+  return launch_tc_cfg<128, 3, PASSES>(a, b, g);
+}
+
 template <class AL, class BL>
 static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return B200RL_OK;
   B200RL_CHECK_ARG(g.K > 0, "gemm: K must be > 0");
   B200RL_CHECK_ARG(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "gemm: dims");
+  const int mode = gemm_mode();
+  if (mode != 0 && g.N >= 16 && g.M >= 32) {
+    if (mode == 2) return launch_tc<1>(a, b, g);
+    return launch_tc<3>(a, b, g);
+  }
   if (g.N <= 32) return launch_gemm_cfg<128, 32, 4, 4>(a, b, g);
   if (g.N <= 64) {
     if (g.M >= 4096) return launch_gemm_cfg<128, 64, 8, 4>(a, b, g);
@@ -441,6 +512,13 @@ static int make_geom(const b200rl_conv_t* c, ConvGeom& g) {
 using namespace b200rl;
 
 extern "C" {
+
+int b200rl_set_gemm_mode(int mode) {
+  B200RL_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32) "
+                                           "or 2 (tcgen05 1xTF32)");
+  g_gemm_mode = mode;
+  return B200RL_OK;
+}
 
 int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y,
                      int64_t M, int64_t K, int64_t N, int act, void* workspace,

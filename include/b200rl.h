@@ -268,6 +268,12 @@ int b200rl_concat2(const float* a, int64_t lda, int64_t da, const float* b, int6
  * through TensorFlow (networks/encoding_network.py:224-312, q_network.py:126-135).
  * All matrices are row-major.
  * ------------------------------------------------------------------------------------ */
+/* GEMM engine for every dense / conv entry point below: 0 = fp32 FFMA register-tiled kernel,
+ * 1 = tcgen05 tensor cores with the 3xTF32 split (fp32-grade accuracy, TMEM accumulators),
+ * 2 = tcgen05 single-pass TF32 (~1e-3 relative; NOT within the 1e-5 parity bar).
+ * Default: env B200RL_GEMM_MODE, else 0.  Outputs narrower than 16 columns always use mode 0. */
+int b200rl_set_gemm_mode(int mode);
+
 /* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
  * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of
  * ws_bytes (may be NULL when ws_bytes==0; then split-K is disabled). */
