@@ -45,36 +45,62 @@ struct FastDiv {
   }
 };
 
+// Operand views.  Every view is separable: element (row, k) lives at row_off(row) + k_off(k),
+// where "row" is m for A views and n for B views.  kKContig says which index is contiguous in
+// memory (4 consecutive k can then be fetched with one 16-byte / 4-byte vector load when
+// vec4_ok()).  `at` is the scalar accessor used by the fp32 FFMA kernel.
 struct ARow {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = true;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[m * ld + k]; }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return m * ld; }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
+  __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
+  __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
 };
 struct ACol {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return m; }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
+  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
 };
-struct BRow {
+struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   const float* p;
   int64_t ld;
   static constexpr bool kNContig = true;
+  static constexpr bool kKContig = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
+  __device__ __forceinline__ int64_t row_off(int64_t n) const { return n; }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
+  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
 };
-struct BCol {
+struct BCol {  // B(k, n) = p[n*ld + k]  (k contiguous)
   const float* p;
   int64_t ld;
   static constexpr bool kNContig = false;
+  static constexpr bool kKContig = true;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[n * ld + k]; }
+  __device__ __forceinline__ int64_t row_off(int64_t n) const { return n * ld; }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
+  __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
+  __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
 };
 
 struct ConvGeom {
   int H, W, C, KH, KW, F, stride, OH, OW;
   FastDiv d_ohow, d_ow, d_kwc;
   int64_t in_row;   // W*C
-  int64_t in_img;   // H*W*C
+  int64_t in_img;   // elements between consecutive images
 };
 
 template <typename T>
@@ -106,7 +132,21 @@ struct ConvView {
     return (int64_t)ky * g.in_row + r;
   }
   __device__ __forceinline__ float load(int64_t off) const { return cvt_in<T>(x[off], scale); }
+  __device__ __forceinline__ bool vec4_ok() const {
+    return (g.C & 3) == 0 && (g.in_img & 3) == 0 && ((uintptr_t)x & (4 * sizeof(T) - 1)) == 0;
+  }
+  __device__ __forceinline__ float4 load4(int64_t off) const;
 };
+template <>
+__device__ __forceinline__ float4 ConvView<float>::load4(int64_t off) const {
+  return *reinterpret_cast<const float4*>(x + off);
+}
+template <>
+__device__ __forceinline__ float4 ConvView<uint8_t>::load4(int64_t off) const {
+  const uchar4 u = *reinterpret_cast<const uchar4*>(x + off);
+  return make_float4(__fdiv_rn((float)u.x, scale), __fdiv_rn((float)u.y, scale),
+                     __fdiv_rn((float)u.z, scale), __fdiv_rn((float)u.w, scale));
+}
 template <typename T>
 struct AConv {
   ConvView<T> v;
@@ -114,6 +154,11 @@ struct AConv {
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)m) + v.patch_offset((uint32_t)k));
   }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.pos_offset((uint32_t)m); }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return v.patch_offset((uint32_t)k); }
+  __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
+  __device__ __forceinline__ float ld1(int64_t off) const { return v.load(off); }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return v.load4(off); }
 };
 template <typename T>
 struct AConvT {
@@ -122,6 +167,11 @@ struct AConvT {
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)k) + v.patch_offset((uint32_t)m));
   }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.patch_offset((uint32_t)m); }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return v.pos_offset((uint32_t)k); }
+  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ float ld1(int64_t off) const { return v.load(off); }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -447,7 +497,7 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
   if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES>(a, b, g);
-  if (g.N <= 64) return launch_tc_cfg<64, 4, PASSES>(a, b, g);
+  if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES>(a, b, g);  // 96 KB -> 2 CTAs / SM
   return launch_tc_cfg<128, 3, PASSES>(a, b, g);
 }
 
@@ -512,6 +562,15 @@ static int make_geom(const b200rl_conv_t* c, ConvGeom& g) {
 using namespace b200rl;
 
 extern "C" {
+
+int b200rl_tc_debug_buffer(long long* dev_buf) {
+  cudaError_t e = cudaMemcpyToSymbol(tc::g_tc_dbg, &dev_buf, sizeof(dev_buf));
+  if (e != cudaSuccess) {
+    set_error("tc_debug_buffer: %s", cudaGetErrorString(e));
+    return B200RL_ERR_CUDA;
+  }
+  return B200RL_OK;
+}
 
 int b200rl_set_gemm_mode(int mode) {
   B200RL_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32) "

@@ -272,14 +272,17 @@ __global__ void __launch_bounds__(32) row_copy_tma(const __grid_constant__ Plan 
           "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
           ::"r"(st_a), "l"(src), "r"(n), "r"(bar_a)
           : "memory");
-      asm volatile(
-          "{\n\t.reg .pred p;\n\t"
-          "WAIT_%=:\n\t"
-          "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], 0;\n\t"
-          "@p bra DONE_%=;\n\t"
-          "bra WAIT_%=;\n\t"
-          "DONE_%=:\n\t}" ::"r"(bar_a)
-          : "memory");
+      // non-blocking poll (mbarrier.try_wait may suspend the thread for a system time limit)
+      uint32_t landed;
+      do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], 0;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(landed)
+            : "r"(bar_a)
+            : "memory");
+      } while (!landed);
       asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
                    "r"(st_a), "r"(n)
                    : "memory");

@@ -8,15 +8,15 @@
 // bits cleared and lo = x - hi (exact); the tensor core accumulates lo_a*hi_b + hi_a*lo_b +
 // hi_a*hi_b into the same fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative).
 //
-// Structure (one CTA = one 128 x BN output tile, cta_group::1):
-//   warps 0-3  producers: gather a (128 x 32) A tile and a (BN x 32) B^T tile of fp32 through
+// Structure (one CTA = one 128 x BN output tile, cta_group::1, 9 warps):
+//   warps 0-7  producers: gather a (128 x 32) A tile and a (BN x 32) B^T tile of fp32 through
 //              the operand views (implicit im2col, u8->f32 cast, transposes all happen here),
 //              split hi/lo, store them K-major into 128B-swizzled shared memory (the layout a
 //              TMA SWIZZLE_128B load would produce), fence.proxy.async, arrive on full[s];
 //              after the main loop the same 4 warps are the epilogue (tcgen05.ld 32x32b:
 //              warp w owns TMEM lanes 32w..32w+31), apply bias/activation, store C or the
 //              split-K partial.
-//   warp 4     allocates TMEM (BN fp32 columns), lane 0 issues tcgen05.mma for every K step
+//   warp 8     allocates TMEM (BN fp32 columns), lane 0 issues tcgen05.mma for every K step
 //              (K = 8 per instruction for tf32; 4 steps x 3 passes per 32-wide K block),
 //              releases stages with tcgen05.commit -> empty[s], signals the epilogue with a
 //              final commit.
@@ -31,8 +31,22 @@ namespace tc {
 
 constexpr int kBM = 128;
 constexpr int kBK = 32;                    // fp32 elements = 128 bytes = one swizzle row
-constexpr int kProducerThreads = 128;
-constexpr int kThreads = 160;
+constexpr int kProducerThreads = 256;
+constexpr int kThreads = 288;
+
+// optional phase stamps (b200rl_tc_debug_buffer): [block][8] nanosecond timers
+__device__ long long* g_tc_dbg = nullptr;
+__device__ __forceinline__ long long gtimer() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void stamp(int slot) {
+  if (g_tc_dbg) {
+    const int64_t blk = blockIdx.x + (int64_t)gridDim.x * (blockIdx.y + (int64_t)gridDim.y * blockIdx.z);
+    if (blk < 64) g_tc_dbg[blk * 8 + slot] = gtimer();
+  }
+}
 
 __device__ __forceinline__ uint32_t smem_addr(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -43,15 +57,19 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// Non-blocking poll: mbarrier.try_wait may suspend the thread for a system-dependent time and
+// measured ~65 us per wait on barriers completed by tcgen05.commit (profiles/README.md, r1 v0).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra D_%=;\n\t"
-      "bra W_%=;\n\t"
-      "D_%=:\n\t}" ::"r"(bar), "r"(parity)
-      : "memory");
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
 }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -86,15 +104,16 @@ __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t j) {
   return (r >> 3) * 1024u + (r & 7u) * 128u + ((j ^ (r & 7u)) << 4);
 }
 
+template <bool WITH_LO>
 __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned char* lo_tile,
-                                            uint32_t off, float4 v, bool with_lo) {
+                                            uint32_t off, float4 v) {
   float4 h;
   h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
   h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
   h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
   h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
   *reinterpret_cast<float4*>(hi_tile + off) = h;
-  if (with_lo) {
+  if (WITH_LO) {
     float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
     *reinterpret_cast<float4*>(lo_tile + off) = l;
   }
@@ -109,7 +128,66 @@ struct SmemLayout {
   static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
-// AL::at(m, k) / BL::at(k, n) are the fp32 operand views of nn.cu.
+// One chunk = 4 consecutive k of one row.  roff = view.row_off(row); koff[i] = view.k_off(k+i).
+template <class V>
+__device__ __forceinline__ float4 load_chunk(const V& v, int64_t roff, bool row_ok, int64_t k,
+                                             int64_t ke, const int64_t (&koff)[4], bool full_vec) {
+  float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (!row_ok || k >= ke) return r;
+  if (V::kKContig && full_vec) return v.ld4(roff + koff[0]);
+  r.x = v.ld1(roff + koff[0]);
+  if (k + 1 < ke) r.y = v.ld1(roff + koff[1]);
+  if (k + 2 < ke) r.z = v.ld1(roff + koff[2]);
+  if (k + 3 < ke) r.w = v.ld1(roff + koff[3]);
+  return r;
+}
+
+// Fills one [ROWS x 32] fp32 operand tile (hi and lo planes) for the K block starting at k0.
+// K-contiguous views: thread = (row group tid>>3, chunk tid&7), 8 lanes read 128 contiguous
+// bytes of a row; row_offs[i] belongs to row (tid>>3) + 32 i.  Other views: thread = (row
+// tid % ROWS, chunks tid/ROWS + TPR i): consecutive lanes read consecutive rows (coalesced) and
+// the XOR swizzle makes the 16-byte stores of 8 consecutive rows hit 8 distinct bank groups.
+template <int ROWS, bool WITH_LO, class V>
+__device__ __forceinline__ void fill_tile(const V& v, unsigned char* hi, unsigned char* lo,
+                                          const int64_t* row_offs, uint32_t row_ok_mask,
+                                          int64_t k0, int64_t ke, bool vec, int tid) {
+  if (V::kKContig) {
+    constexpr int NR = ROWS * 8 / kProducerThreads;
+    const int j = tid & 7;
+    const int64_t k = k0 + j * 4;
+    const bool full_vec = vec && (k + 3 < ke);
+    int64_t koff[4];
+    koff[0] = k < ke ? v.k_off(k) : 0;
+#pragma unroll
+    for (int i = 1; i < 4; ++i) koff[i] = (!full_vec && k + i < ke) ? v.k_off(k + i) : 0;
+    float4 val[NR];
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      val[i] = load_chunk(v, row_offs[i], (row_ok_mask >> i) & 1u, k, ke, koff, full_vec);
+#pragma unroll
+    for (int i = 0; i < NR; ++i)
+      split_store<WITH_LO>(hi, lo, sw128((uint32_t)((tid >> 3) + 32 * i), (uint32_t)j), val[i]);
+  } else {
+    constexpr int TPR = kProducerThreads / ROWS;  // threads per row
+    constexpr int NJ = 8 / TPR;                   // chunks per thread
+    const int r = tid % ROWS;
+    const int jb = tid / ROWS;
+    float4 val[NJ];
+#pragma unroll
+    for (int i = 0; i < NJ; ++i) {
+      const int64_t k = k0 + (jb + TPR * i) * 4;
+      int64_t koff[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) koff[q] = (k + q < ke) ? v.k_off(k + q) : 0;
+      val[i] = load_chunk(v, row_offs[0], row_ok_mask & 1u, k, ke, koff, false);
+    }
+#pragma unroll
+    for (int i = 0; i < NJ; ++i)
+      split_store<WITH_LO>(hi, lo, sw128((uint32_t)r, (uint32_t)(jb + TPR * i)), val[i]);
+  }
+}
+
+// AL / BL are the fp32 operand views of nn.cu (row index = m for A, n for B).
 template <int BN, int STAGES, int PASSES, class AL, class BL>
 __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL b,
                                                            float* __restrict__ C,
@@ -135,15 +213,16 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
   const int64_t ke = (kb + k_per_split < K) ? kb + k_per_split : K;
   const int nkb = (int)((ke - kb + kBK - 1) / kBK);
 
+  if (tid == 0) stamp(0);
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(smem_addr(&full[s]), 4);    // one arrive per producer warp
+      mbar_init(smem_addr(&full[s]), kProducerThreads / 32);  // one arrive per producer warp
       mbar_init(smem_addr(&empty[s]), 1);   // tcgen05.commit
     }
     mbar_init(smem_addr(accum), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) {
+  if (warp == 8) {
     constexpr int kCols = BN < 32 ? 32 : BN;
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_addr(tmem_slot)),
@@ -154,9 +233,31 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  if (tid == 0) stamp(1);
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ===================== producers =====================
+    constexpr bool kLo = PASSES == 3;
+    constexpr int NRA = AL::kKContig ? kBM * 8 / kProducerThreads : 1;
+    constexpr int NRB = BL::kKContig ? BN * 8 / kProducerThreads : 1;
+    static_assert(BN * 8 >= kProducerThreads, "BN must be >= 32");
+    int64_t a_off[NRA], b_off[NRB];
+    uint32_t a_ok = 0, b_ok = 0;
+#pragma unroll
+    for (int i = 0; i < NRA; ++i) {  // hoisted row offsets (implicit-im2col index math runs once)
+      const int r = AL::kKContig ? (tid >> 3) + 32 * i : tid % kBM;
+      const bool ok = m0 + r < M;
+      a_off[i] = ok ? a.row_off(m0 + r) : 0;
+      a_ok |= (ok ? 1u : 0u) << i;
+    }
+#pragma unroll
+    for (int i = 0; i < NRB; ++i) {
+      const int r = BL::kKContig ? (tid >> 3) + 32 * i : tid % BN;
+      const bool ok = n0 + r < N;
+      b_off[i] = ok ? b.row_off(n0 + r) : 0;
+      b_ok |= (ok ? 1u : 0u) << i;
+    }
+    const bool a_vec = a.vec4_ok(), b_vec = b.vec4_ok();
     for (int kbi = 0; kbi < nkb; ++kbi) {
       const int s = kbi % STAGES;
       const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
@@ -167,75 +268,57 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
       unsigned char* b_hi = st + L::kNumA * L::kATile;
       unsigned char* b_lo = b_hi + L::kBTile;
       const int64_t k0 = kb + (int64_t)kbi * kBK;
-      // A tile: 128 rows x 8 chunks; 8 consecutive threads cover one row (128 contiguous bytes
-      // for K-contiguous views)
-#pragma unroll 4
-      for (int i = tid; i < kBM * 8; i += kProducerThreads) {
-        const int r = i >> 3, j = i & 7;
-        const int64_t m = m0 + r, k = k0 + j * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < M) {
-          if (k + 0 < ke) v.x = a.at(m, k + 0);
-          if (k + 1 < ke) v.y = a.at(m, k + 1);
-          if (k + 2 < ke) v.z = a.at(m, k + 2);
-          if (k + 3 < ke) v.w = a.at(m, k + 3);
-        }
-        split_store(a_hi, a_lo, sw128(r, j), v, PASSES == 3);
-      }
-#pragma unroll 2
-      for (int i = tid; i < BN * 8; i += kProducerThreads) {
-        const int r = i >> 3, j = i & 7;
-        const int64_t n = n0 + r, k = k0 + j * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (n < N) {
-          if (k + 0 < ke) v.x = b.at(k + 0, n);
-          if (k + 1 < ke) v.y = b.at(k + 1, n);
-          if (k + 2 < ke) v.z = b.at(k + 2, n);
-          if (k + 3 < ke) v.w = b.at(k + 3, n);
-        }
-        split_store(b_hi, b_lo, sw128(r, j), v, PASSES == 3);
-      }
+      fill_tile<kBM, kLo>(a, a_hi, a_lo, a_off, a_ok, k0, ke, a_vec, tid);
+      fill_tile<BN, kLo>(b, b_hi, b_lo, b_off, b_ok, k0, ke, b_vec, tid);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&full[s]));
     }
     // ===================== epilogue =====================
+    if (tid == 0) stamp(2);
     mbar_wait(smem_addr(accum), 0u);
+    if (tid == 0) stamp(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int64_t m = m0 + warp * 32 + lane;
+    const int q = warp & 3, half = warp >> 2;   // TMEM lane quadrant / column half of this warp
+    const int64_t m = m0 + q * 32 + lane;
     float* out = (splits > 1) ? ws + (int64_t)split * M * N : C;
+    const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
 #pragma unroll
-    for (int c = 0; c < BN; c += 8) {
+    for (int cc = 0; cc < BN / 2; cc += 8) {
+      const int c = half * (BN / 2) + cc;
       uint32_t r[8];
-      const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
           : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
             "=r"(r[7])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m < M && nkb > 0) {
+      if (m >= M) continue;
+      const int64_t nb = n0 + c;
+      float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t n = n0 + c + j;
-          if (n >= N) continue;
-          float v = __uint_as_float(r[j]);
-          if (splits == 1) {
-            if (bias) v += bias[n];
-            v = apply_act(v, act);
-            if (beta) v += out[m * N + n];
-          }
-          out[m * N + n] = v;
+      for (int j = 0; j < 8; ++j) {
+        float x = nkb > 0 ? __uint_as_float(r[j]) : 0.f;
+        if (splits == 1 && nb + j < N) {
+          if (bias) x += bias[nb + j];
+          x = apply_act(x, act);
+          if (beta) x += out[m * N + nb + j];
         }
-      } else if (m < M && nkb == 0) {
+        v[j] = x;
+      }
+      if (vec_out && nb + 7 < N) {
+        float4* dst = reinterpret_cast<float4*>(out + m * N + nb);
+        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+      } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int64_t n = n0 + c + j;
-          if (n < N) out[m * N + n] = 0.f;
-        }
+        for (int j = 0; j < 8; ++j)
+          if (nb + j < N) out[m * N + nb + j] = v[j];
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    if (tid == 0) stamp(5);
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0) {
@@ -263,15 +346,17 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
         tc_commit(smem_addr(&empty[s]));
       }
       tc_commit(smem_addr(accum));
+      stamp(3);
     }
     __syncwarp();
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     constexpr int kCols = BN < 32 ? 32 : BN;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "n"(kCols));
+    if (lane == 0) stamp(6);
   }
 }
 

@@ -273,6 +273,9 @@ int b200rl_concat2(const float* a, int64_t lda, int64_t da, const float* b, int6
  * 2 = tcgen05 single-pass TF32 (~1e-3 relative; NOT within the 1e-5 parity bar).
  * Default: env B200RL_GEMM_MODE, else 0.  Outputs narrower than 16 columns always use mode 0. */
 int b200rl_set_gemm_mode(int mode);
+/* Profiling aid: device buffer of int64[64][8] that receives %globaltimer phase stamps of the
+ * first 64 CTAs of every tcgen05 GEMM launch (NULL disables). */
+int b200rl_tc_debug_buffer(long long* dev_buf);
 
 /* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
  * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of
