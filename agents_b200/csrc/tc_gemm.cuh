@@ -142,17 +142,19 @@ __device__ __forceinline__ float4 load_chunk(const V& v, int64_t roff, bool row_
   return r;
 }
 
-// Fills one [ROWS x 32] fp32 operand tile (hi and lo planes) for the K block starting at k0.
+// A [ROWS x 32] fp32 operand tile is moved in two steps so that the global loads of K block i+1
+// are in flight while block i is split and stored: gather_tile (global -> registers) and
+// scatter_tile (registers -> hi/lo planes in 128B-swizzled shared memory).
 // K-contiguous views: thread = (row group tid>>3, chunk tid&7), 8 lanes read 128 contiguous
 // bytes of a row; row_offs[i] belongs to row (tid>>3) + 32 i.  Other views: thread = (row
 // tid % ROWS, chunks tid/ROWS + TPR i): consecutive lanes read consecutive rows (coalesced) and
 // the XOR swizzle makes the 16-byte stores of 8 consecutive rows hit 8 distinct bank groups.
-template <int ROWS, bool WITH_LO, class V>
-__device__ __forceinline__ void fill_tile(const V& v, unsigned char* hi, unsigned char* lo,
-                                          const int64_t* row_offs, uint32_t row_ok_mask,
-                                          int64_t k0, int64_t ke, bool vec, int tid) {
+template <int ROWS, class V>
+__device__ __forceinline__ void gather_tile(const V& v, const int64_t* row_offs,
+                                            uint32_t row_ok_mask, int64_t k0, int64_t ke, bool vec,
+                                            int tid, float4 (&val)[ROWS * 8 / kProducerThreads]) {
+  constexpr int NV = ROWS * 8 / kProducerThreads;
   if (V::kKContig) {
-    constexpr int NR = ROWS * 8 / kProducerThreads;
     const int j = tid & 7;
     const int64_t k = k0 + j * 4;
     const bool full_vec = vec && (k + 3 < ke);
@@ -160,36 +162,42 @@ __device__ __forceinline__ void fill_tile(const V& v, unsigned char* hi, unsigne
     koff[0] = k < ke ? v.k_off(k) : 0;
 #pragma unroll
     for (int i = 1; i < 4; ++i) koff[i] = (!full_vec && k + i < ke) ? v.k_off(k + i) : 0;
-    float4 val[NR];
 #pragma unroll
-    for (int i = 0; i < NR; ++i)
+    for (int i = 0; i < NV; ++i)
       val[i] = load_chunk(v, row_offs[i], (row_ok_mask >> i) & 1u, k, ke, koff, full_vec);
-#pragma unroll
-    for (int i = 0; i < NR; ++i)
-      split_store<WITH_LO>(hi, lo, sw128((uint32_t)((tid >> 3) + 32 * i), (uint32_t)j), val[i]);
   } else {
     constexpr int TPR = kProducerThreads / ROWS;  // threads per row
-    constexpr int NJ = 8 / TPR;                   // chunks per thread
-    const int r = tid % ROWS;
     const int jb = tid / ROWS;
-    float4 val[NJ];
 #pragma unroll
-    for (int i = 0; i < NJ; ++i) {
+    for (int i = 0; i < NV; ++i) {
       const int64_t k = k0 + (jb + TPR * i) * 4;
       int64_t koff[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) koff[q] = (k + q < ke) ? v.k_off(k + q) : 0;
       val[i] = load_chunk(v, row_offs[0], row_ok_mask & 1u, k, ke, koff, false);
     }
+  }
+}
+
+template <int ROWS, bool WITH_LO, bool KCONTIG>
+__device__ __forceinline__ void scatter_tile(unsigned char* hi, unsigned char* lo, int tid,
+                                             const float4 (&val)[ROWS * 8 / kProducerThreads]) {
+  constexpr int NV = ROWS * 8 / kProducerThreads;
+  if (KCONTIG) {
 #pragma unroll
-    for (int i = 0; i < NJ; ++i)
-      split_store<WITH_LO>(hi, lo, sw128((uint32_t)r, (uint32_t)(jb + TPR * i)), val[i]);
+    for (int i = 0; i < NV; ++i)
+      split_store<WITH_LO>(hi, lo, sw128((uint32_t)((tid >> 3) + 32 * i), (uint32_t)(tid & 7)), val[i]);
+  } else {
+    constexpr int TPR = kProducerThreads / ROWS;
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      split_store<WITH_LO>(hi, lo, sw128((uint32_t)(tid % ROWS), (uint32_t)(tid / ROWS + TPR * i)), val[i]);
   }
 }
 
 // AL / BL are the fp32 operand views of nn.cu (row index = m for A, n for B).
 template <int BN, int STAGES, int PASSES, class AL, class BL>
-__global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL b,
+__global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const AL a, const BL b,
                                                            float* __restrict__ C,
                                                            const float* __restrict__ bias,
                                                            int64_t M, int64_t N, int64_t K, int act,
@@ -258,21 +266,35 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
       b_ok |= (ok ? 1u : 0u) << i;
     }
     const bool a_vec = a.vec4_ok(), b_vec = b.vec4_ok();
+    constexpr int NVA = kBM * 8 / kProducerThreads, NVB = BN * 8 / kProducerThreads;
+    float4 av[NVA], bv[NVB], an[NVA], bn[NVB];
+    if (nkb > 0) {
+      gather_tile<kBM>(a, a_off, a_ok, kb, ke, a_vec, tid, av);
+      gather_tile<BN>(b, b_off, b_ok, kb, ke, b_vec, tid, bv);
+    }
     for (int kbi = 0; kbi < nkb; ++kbi) {
       const int s = kbi % STAGES;
       const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
+      if (kbi + 1 < nkb) {  // issue the next block's global loads before touching shared memory
+        const int64_t k1 = kb + (int64_t)(kbi + 1) * kBK;
+        gather_tile<kBM>(a, a_off, a_ok, k1, ke, a_vec, tid, an);
+        gather_tile<BN>(b, b_off, b_ok, k1, ke, b_vec, tid, bn);
+      }
       if (kbi >= STAGES) mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
       unsigned char* st = smem + s * L::kStage;
       unsigned char* a_hi = st;
       unsigned char* a_lo = st + L::kATile;
       unsigned char* b_hi = st + L::kNumA * L::kATile;
       unsigned char* b_lo = b_hi + L::kBTile;
-      const int64_t k0 = kb + (int64_t)kbi * kBK;
-      fill_tile<kBM, kLo>(a, a_hi, a_lo, a_off, a_ok, k0, ke, a_vec, tid);
-      fill_tile<BN, kLo>(b, b_hi, b_lo, b_off, b_ok, k0, ke, b_vec, tid);
+      scatter_tile<kBM, kLo, AL::kKContig>(a_hi, a_lo, tid, av);
+      scatter_tile<BN, kLo, BL::kKContig>(b_hi, b_lo, tid, bv);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&full[s]));
+#pragma unroll
+      for (int i = 0; i < NVA; ++i) av[i] = an[i];
+#pragma unroll
+      for (int i = 0; i < NVB; ++i) bv[i] = bn[i];
     }
     // ===================== epilogue =====================
     if (tid == 0) stamp(2);
@@ -283,22 +305,25 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
     const int64_t m = m0 + q * 32 + lane;
     float* out = (splits > 1) ? ws + (int64_t)split * M * N : C;
     const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
+    constexpr int G = 16;  // columns fetched per tcgen05.ld
 #pragma unroll
-    for (int cc = 0; cc < BN / 2; cc += 8) {
+    for (int cc = 0; cc < BN / 2; cc += G) {
       const int c = half * (BN / 2) + cc;
-      uint32_t r[8];
+      uint32_t r[G];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
           : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-            "=r"(r[7])
+            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+            "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (m >= M) continue;
       const int64_t nb = n0 + c;
-      float v[8];
+      float v[G];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < G; ++j) {
         float x = nkb > 0 ? __uint_as_float(r[j]) : 0.f;
         if (splits == 1 && nb + j < N) {
           if (bias) x += bias[nb + j];
@@ -307,13 +332,13 @@ __global__ void __launch_bounds__(kThreads) tc_gemm_kernel(const AL a, const BL 
         }
         v[j] = x;
       }
-      if (vec_out && nb + 7 < N) {
+      if (vec_out && nb + G - 1 < N) {
         float4* dst = reinterpret_cast<float4*>(out + m * N + nb);
-        dst[0] = make_float4(v[0], v[1], v[2], v[3]);
-        dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+#pragma unroll
+        for (int j = 0; j < G / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
       } else {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
+        for (int j = 0; j < G; ++j)
           if (nb + j < N) out[m * N + nb + j] = v[j];
       }
     }
