@@ -385,15 +385,11 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict_
   const int y = (int)(r % g.H);
   const int64_t n = r / g.H;
   float s = 0.f;
-  for (int ky = 0; ky < g.KH; ++ky) {
-    const int ty = y - ky;
-    if (ty < 0 || ty % g.stride) continue;
-    const int oy = ty / g.stride;
+  for (int ky = y % g.stride; ky < g.KH && ky <= y; ky += g.stride) {
+    const int oy = (y - ky) / g.stride;
     if (oy >= g.OH) continue;
-    for (int kx = 0; kx < g.KW; ++kx) {
-      const int tx = x - kx;
-      if (tx < 0 || tx % g.stride) continue;
-      const int ox = tx / g.stride;
+    for (int kx = x % g.stride; kx < g.KW && kx <= x; kx += g.stride) {
+      const int ox = (x - kx) / g.stride;
       if (ox >= g.OW) continue;
       const int64_t pos = (n * g.OH + oy) * g.OW + ox;
       s += dcol[pos * Kc + (ky * g.KW + kx) * g.C + c];
@@ -454,7 +450,7 @@ static int g_gemm_mode = -1;
 static int gemm_mode() {
   if (g_gemm_mode < 0) {
     const char* e = getenv("B200RL_GEMM_MODE");
-    g_gemm_mode = e ? atoi(e) : 0;
+    g_gemm_mode = e ? atoi(e) : 1;
   }
   return g_gemm_mode;
 }
@@ -505,7 +501,7 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
 
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
-  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES>(a, b, g);
+  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES>(a, b, g);  // 80 KB -> 2 CTAs / SM
   if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES>(a, b, g);  // 96 KB -> 2 CTAs / SM
   return launch_tc_cfg<128, 3, PASSES>(a, b, g);
 }

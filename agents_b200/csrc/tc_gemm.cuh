@@ -168,12 +168,17 @@ __device__ __forceinline__ void gather_tile(const V& v, const int64_t* row_offs,
   } else {
     constexpr int TPR = kProducerThreads / ROWS;  // threads per row
     const int jb = tid / ROWS;
+    // k_off depends on k only (for the conv filter-gradient view it is a full (n, oy, ox) decode):
+    // lane l computes it for k0 + l once and the 4 offsets of each chunk are fetched by shuffle.
+    const int lane = tid & 31;
+    const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      const int64_t k = k0 + (jb + TPR * i) * 4;
+      const int j = jb + TPR * i;
+      const int64_t k = k0 + j * 4;
       int64_t koff[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) koff[q] = (k + q < ke) ? v.k_off(k + q) : 0;
+      for (int q = 0; q < 4; ++q) koff[q] = __shfl_sync(0xffffffffu, my_koff, j * 4 + q);
       val[i] = load_chunk(v, row_offs[0], row_ok_mask & 1u, k, ke, koff, false);
     }
   }

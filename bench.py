@@ -394,7 +394,7 @@ def main():
     line = dict(
         metric='train steps/sec (DQN Atari-shape, batch 256)', value=value, unit='steps/s',
         n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
-        scaling='weak', vs_baseline=None, dtype='f32', data='synthetic',
+        scaling='weak', vs_baseline=None, dtype='f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)', data='synthetic',
         config=dict(workload='DQN synthetic Atari-shape obs 84x84x4 uint8, 1M-slot replay '
                              f'({B_ENV}x{L}), batch {B}, T={T}, Mnih15 net, Huber, centered RMSProp',
                     global_batch=B * world, per_gpu_batch=B, num_actions=A,
@@ -405,7 +405,7 @@ def main():
         e2e=dict(value=e2e_value, unit='steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                  steps=Ke),
         gpu_launches=int(launches_per_step * K),
-        roofline=dict(kernel='sgemm_kernel (Q-net conv/dense fwd+bwd, fp32 FFMA)', bound='tensor',
+        roofline=dict(kernel='tc_gemm_kernel (Q-net conv/dense fwd+bwd, tcgen05 kind::tf32, 3xTF32)', bound='tensor',
                       achieved=update_tfs, peak=peaks['tensor'], unit='TFLOP/s',
                       frac=update_tfs / peaks['tensor'], traffic=traffic.get('update'),
                       peak_source=peaks['src'] + ' bf16 sustained', ms=update_ms,

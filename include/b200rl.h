@@ -271,7 +271,8 @@ int b200rl_concat2(const float* a, int64_t lda, int64_t da, const float* b, int6
 /* GEMM engine for every dense / conv entry point below: 0 = fp32 FFMA register-tiled kernel,
  * 1 = tcgen05 tensor cores with the 3xTF32 split (fp32-grade accuracy, TMEM accumulators),
  * 2 = tcgen05 single-pass TF32 (~1e-3 relative; NOT within the 1e-5 parity bar).
- * Default: env B200RL_GEMM_MODE, else 0.  Outputs narrower than 16 columns always use mode 0. */
+ * Default: env B200RL_GEMM_MODE, else 1.  Outputs narrower than 16 columns (Q head, value head)
+ * always use mode 0. */
 int b200rl_set_gemm_mode(int mode);
 /* Profiling aid: device buffer of int64[64][8] that receives %globaltimer phase stamps of the
  * first 64 CTAs of every tcgen05 GEMM launch (NULL disables). */
