@@ -67,9 +67,9 @@ struct ACol {
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return m; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
-  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
-  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
 };
 struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   const float* p;
@@ -79,9 +79,9 @@ struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
   __device__ __forceinline__ int64_t row_off(int64_t n) const { return n; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
-  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
-  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
 };
 struct BCol {  // B(k, n) = p[n*ld + k]  (k contiguous)
   const float* p;
@@ -178,9 +178,9 @@ struct AConvT {
   }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.patch_offset((uint32_t)m); }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return v.pos_offset((uint32_t)k); }
-  __device__ __forceinline__ bool vec4_ok() const { return false; }
+  __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
   __device__ __forceinline__ float ld1(int64_t off) const { return v.load_fast(off); }
-  __device__ __forceinline__ float4 ld4(int64_t off) const { return make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ float4 ld4(int64_t off) const { return v.load4(off); }
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {

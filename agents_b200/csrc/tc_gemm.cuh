@@ -95,8 +95,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
   return d;
 }
-__host__ __device__ constexpr uint32_t make_idesc(int bn) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+// MN-major, SWIZZLE_128B (cute canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
+// a k-row holds 32 consecutive M/N elements (128 B), 8 k-rows form a 1024 B swizzle atom,
+// LBO = distance between 32-element M/N groups, SBO = distance between 8-row k groups.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc(int bn, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn ? 1u : 0u) << 15) | ((b_mn ? 1u : 0u) << 16) |
+         ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
+}
+// byte offset of the 16-byte chunk holding rows 4*cm..4*cm+3 at reduction index k (0..31) in an
+// MN-major tile of ROWS rows: groups of 32 rows are kGroup apart, k groups of 8 are 1024 B apart
+template <int ROWS>
+__device__ __forceinline__ uint32_t mn128(uint32_t cm, uint32_t k) {
+  return (cm >> 3) * 4096u + (k >> 3) * 1024u + (k & 7u) * 128u + (((cm & 7u) ^ (k & 7u)) << 4);
 }
 
 // byte offset of 16-byte chunk j (0..7) of row r inside a [rows x 128 B] swizzled tile
@@ -182,6 +201,50 @@ __device__ __forceinline__ void gather_tile(const V& v, const int64_t* row_offs,
       val[i] = load_chunk(v, row_offs[0], row_ok_mask & 1u, k, ke, koff, false);
     }
   }
+}
+
+// MN-major tiles (views whose M/N index is contiguous in memory): thread = (row chunk cm =
+// tid % (ROWS/4), k = tid / (ROWS/4) + KSTEP i).  A warp reads up to 512 contiguous bytes of one
+// k-row with 16-byte vectors; no transposition is needed because the MMA descriptor is MN-major.
+template <int ROWS, class V>
+__device__ __forceinline__ void gather_tile_mn(const V& v, int64_t row0, int64_t row_limit,
+                                               int64_t k0, int64_t ke, bool vec, int tid,
+                                               float4 (&val)[ROWS * 8 / kProducerThreads]) {
+  constexpr int NV = ROWS * 8 / kProducerThreads;
+  constexpr int CPR = ROWS / 4;                      // chunks per k-row
+  constexpr int KSTEP = kProducerThreads / CPR;      // k-rows covered per pass
+  const int cm = tid % CPR;
+  const int64_t r = row0 + 4 * cm;
+  const int64_t roff = r < row_limit ? v.row_off(r) : 0;
+  const bool row_full = r + 3 < row_limit;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int64_t k = k0 + tid / CPR + KSTEP * i;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < ke && r < row_limit) {
+      const int64_t off = roff + v.k_off(k);
+      if (vec && row_full) {
+        x = v.ld4(off);
+      } else {
+        x.x = v.ld1(off);
+        if (r + 1 < row_limit) x.y = v.ld1(v.row_off(r + 1) + v.k_off(k));
+        if (r + 2 < row_limit) x.z = v.ld1(v.row_off(r + 2) + v.k_off(k));
+        if (r + 3 < row_limit) x.w = v.ld1(v.row_off(r + 3) + v.k_off(k));
+      }
+    }
+    val[i] = x;
+  }
+}
+
+template <int ROWS, bool WITH_LO>
+__device__ __forceinline__ void scatter_tile_mn(unsigned char* hi, unsigned char* lo, int tid,
+                                                const float4 (&val)[ROWS * 8 / kProducerThreads]) {
+  constexpr int NV = ROWS * 8 / kProducerThreads;
+  constexpr int CPR = ROWS / 4;
+  constexpr int KSTEP = kProducerThreads / CPR;
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+    split_store<WITH_LO>(hi, lo, mn128<ROWS>((uint32_t)(tid % CPR), (uint32_t)(tid / CPR + KSTEP * i)), val[i]);
 }
 
 template <int ROWS, bool WITH_LO, bool KCONTIG>
@@ -273,17 +336,25 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
     const bool a_vec = a.vec4_ok(), b_vec = b.vec4_ok();
     constexpr int NVA = kBM * 8 / kProducerThreads, NVB = BN * 8 / kProducerThreads;
     float4 av[NVA], bv[NVB], an[NVA], bn[NVB];
+    auto gather_a = [&](int64_t k0, float4 (&dst)[NVA]) {
+      if (AL::kKContig) gather_tile<kBM>(a, a_off, a_ok, k0, ke, a_vec, tid, dst);
+      else gather_tile_mn<kBM>(a, m0, M, k0, ke, a_vec, tid, dst);
+    };
+    auto gather_b = [&](int64_t k0, float4 (&dst)[NVB]) {
+      if (BL::kKContig) gather_tile<BN>(b, b_off, b_ok, k0, ke, b_vec, tid, dst);
+      else gather_tile_mn<BN>(b, n0, N, k0, ke, b_vec, tid, dst);
+    };
     if (nkb > 0) {
-      gather_tile<kBM>(a, a_off, a_ok, kb, ke, a_vec, tid, av);
-      gather_tile<BN>(b, b_off, b_ok, kb, ke, b_vec, tid, bv);
+      gather_a(kb, av);
+      gather_b(kb, bv);
     }
     for (int kbi = 0; kbi < nkb; ++kbi) {
       const int s = kbi % STAGES;
       const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
       if (kbi + 1 < nkb) {  // issue the next block's global loads before touching shared memory
         const int64_t k1 = kb + (int64_t)(kbi + 1) * kBK;
-        gather_tile<kBM>(a, a_off, a_ok, k1, ke, a_vec, tid, an);
-        gather_tile<BN>(b, b_off, b_ok, k1, ke, b_vec, tid, bn);
+        gather_a(k1, an);
+        gather_b(k1, bn);
       }
       if (kbi >= STAGES) mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
       unsigned char* st = smem + s * L::kStage;
@@ -291,8 +362,10 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       unsigned char* a_lo = st + L::kATile;
       unsigned char* b_hi = st + L::kNumA * L::kATile;
       unsigned char* b_lo = b_hi + L::kBTile;
-      scatter_tile<kBM, kLo, AL::kKContig>(a_hi, a_lo, tid, av);
-      scatter_tile<BN, kLo, BL::kKContig>(b_hi, b_lo, tid, bv);
+      if (AL::kKContig) scatter_tile<kBM, kLo, true>(a_hi, a_lo, tid, av);
+      else scatter_tile_mn<kBM, kLo>(a_hi, a_lo, tid, av);
+      if (BL::kKContig) scatter_tile<BN, kLo, true>(b_hi, b_lo, tid, bv);
+      else scatter_tile_mn<BN, kLo>(b_hi, b_lo, tid, bv);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&full[s]));
@@ -352,7 +425,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
   } else {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BN);
+      constexpr uint32_t idesc = make_idesc(BN, !AL::kKContig, !BL::kKContig);
       for (int kbi = 0; kbi < nkb; ++kbi) {
         const int s = kbi % STAGES;
         const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
@@ -363,14 +436,18 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
         const uint32_t b_hi = a_hi + L::kNumA * L::kATile, b_lo = b_hi + L::kBTile;
 #pragma unroll
         for (int ks = 0; ks < kBK / 8; ++ks) {
-          const uint32_t koff = (uint32_t)ks * 32u;  // 8 tf32 = 32 bytes inside the 128 B row
+          // K-major: 8 tf32 = 32 bytes further inside the 128 B row; MN-major: next 8-row k group
+          const uint32_t ka = AL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 1024u;
+          const uint32_t kbo = BL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 1024u;
+          auto da = [&](uint32_t base) { return AL::kKContig ? make_desc(base + ka) : make_desc_mn(base + ka, 4096u); };
+          auto db = [&](uint32_t base) { return BL::kKContig ? make_desc(base + kbo) : make_desc_mn(base + kbo, 4096u); };
           const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
           if (PASSES == 3) {
-            tc_mma_tf32(tmem_base, make_desc(a_lo + koff), make_desc(b_hi + koff), idesc, first);
-            tc_mma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_lo + koff), idesc, 1u);
-            tc_mma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, 1u);
+            tc_mma_tf32(tmem_base, da(a_lo), db(b_hi), idesc, first);
+            tc_mma_tf32(tmem_base, da(a_hi), db(b_lo), idesc, 1u);
+            tc_mma_tf32(tmem_base, da(a_hi), db(b_hi), idesc, 1u);
           } else {
-            tc_mma_tf32(tmem_base, make_desc(a_hi + koff), make_desc(b_hi + koff), idesc, first);
+            tc_mma_tf32(tmem_base, da(a_hi), db(b_hi), idesc, first);
           }
         }
         tc_commit(smem_addr(&empty[s]));

@@ -284,10 +284,20 @@ def main():
   torch.cuda.synchronize()
   launches_per_step = _lib.launch_count() - c0
 
-  use_graph = not args.no_graph and world == 1
+  use_graph = not args.no_graph
   fn = common.function(step, warmup=1) if use_graph else step
-  for _ in range(W + 2):
-    fn()
+  try:
+    for _ in range(W + 2):
+      fn()
+  except Exception as e:  # e.g. a collective that cannot be captured on this stack -> eager
+    if not use_graph:
+      raise
+    sys.stderr.write(f'CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n')
+    use_graph = False
+    fn = step
+    torch.cuda.synchronize()
+    for _ in range(W):
+      fn()
   sync_all()
 
   # ---- timed region: K steps, CUDA events, max over ranks ---------------------------------------
