@@ -22,6 +22,8 @@ for p in "${pids[@]:-}"; do
 done
 if [[ $rc -ne 0 ]]; then
   cat "$here"/obj/*.log | grep -E "error|Error" -A3 | head -80
+  echo "BUILD FAILED" >&2
+  rm -f "$out/libb200rl.so"   # never leave a stale library behind a failed build
   exit 1
 fi
 "$NVCC" -shared -gencode arch=compute_100a,code=sm_100a -o "$out/libb200rl.so" "$here"/obj/*.o -lcudart_static -ldl -lrt -lpthread

@@ -577,6 +577,15 @@ int b200rl_tc_debug_buffer(long long* dev_buf) {
   return B200RL_OK;
 }
 
+int b200rl_tc_debug_variant(int v) {
+  cudaError_t e = cudaMemcpyToSymbol(tc::g_tc_variant, &v, sizeof(v));
+  if (e != cudaSuccess) {
+    set_error("tc_debug_variant: %s", cudaGetErrorString(e));
+    return B200RL_ERR_CUDA;
+  }
+  return B200RL_OK;
+}
+
 int b200rl_set_gemm_mode(int mode) {
   B200RL_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32) "
                                            "or 2 (tcgen05 1xTF32)");

@@ -36,6 +36,7 @@ constexpr int kThreads = 288;
 
 // optional phase stamps (b200rl_tc_debug_buffer): [block][8] nanosecond timers
 __device__ long long* g_tc_dbg = nullptr;
+__device__ int g_tc_variant = 0;  // layout experiments for MN-major tiles (profiles/tc_layout_probe.py)
 __device__ __forceinline__ long long gtimer() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -95,16 +96,27 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
   d |= (uint64_t)2 << 61;                          // layout type SWIZZLE_128B
   return d;
 }
-// MN-major, SWIZZLE_128B (cute canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units):
-// a k-row holds 32 consecutive M/N elements (128 B), 8 k-rows form a 1024 B swizzle atom,
-// LBO = distance between 32-element M/N groups, SBO = distance between 8-row k groups.
-__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t lbo_bytes) {
+// MN-major tf32 operands: SWIZZLE_128B_BASE32B is the only layout the tensor core accepts for
+// 32-bit MN-major data (cutlass sm100_common.inl: "for mn-major tf32 operands, SW128_32B is the
+// only available smem layout"; cute Layout_MN_SW128_32B_Atom = Swizzle<2,5,2> o (1024 bit, 4) :
+// (1, 1024 bit)).  A k-row holds 32 consecutive M/N elements (128 B); 4 k-rows form a 512 B atom
+// in which the 32-byte blocks of a row are XORed with the row index; LBO = distance between
+// 32-element M/N groups, SBO = distance between 4-row k atoms (one K=8 MMA spans two atoms).
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(512 >> 4) << 16;                 // LBO: next 32-row M/N group (adjacent atom)
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // SBO: next 4-row k atom = (ROWS/32) atoms
+  d |= (uint64_t)1 << 46;                          // version = 1 (sm_100)
+  const int var = g_tc_variant;
+  const uint64_t lt = (var & 1) ? ((var & 16) ? 0ull : 2ull) : 1ull;
+  d |= lt << 61;                                   // layout type (1 = SWIZZLE_128B_BASE32B)
+  if (var & 8) {                                   // 8-row atoms: LBO 1024, SBO = G * 1024
+    d &= ~((uint64_t)0x3FFF << 16);
+    d |= (uint64_t)(1024 >> 4) << 16;
+    d &= ~((uint64_t)0x3FFF << 32);
+    d |= (uint64_t)(((sbo_bytes * 2) >> 4) & 0x3FFF) << 32;
+  }
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int bn, bool a_mn, bool b_mn) {
@@ -112,13 +124,29 @@ __host__ __device__ constexpr uint32_t make_idesc(int bn, bool a_mn, bool b_mn) 
          ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(kBM >> 4) << 24);
 }
 // byte offset of the 16-byte chunk holding rows 4*cm..4*cm+3 at reduction index k (0..31) in an
-// MN-major tile of ROWS rows: groups of 32 rows are kGroup apart, k groups of 8 are 1024 B apart
+// MN-major tile: 512 B atoms (32 rows x 4 k) tiled M/N-fastest, rows 128 B apart;
+// inside a row the 32-byte block index is XORed with (k & 3).
 template <int ROWS>
 __device__ __forceinline__ uint32_t mn128(uint32_t cm, uint32_t k) {
-  return (cm >> 3) * 4096u + (k >> 3) * 1024u + (k & 7u) * 128u + (((cm & 7u) ^ (k & 7u)) << 4);
+  // atoms are tiled M/N-fastest (the arrangement cute's tile_to_shape produces)
+  const uint32_t c = cm & 7u, kin = k & 3u;
+  const int var = g_tc_variant;
+  const int swz = (var >> 1) & 3;
+  if (var & 8) {  // SW128 (8-row atoms) arrangement: atoms of 8 k rows, M/N-fastest
+    const uint32_t k8 = k & 7u;
+    uint32_t cc = c;
+    if (swz == 2) cc = c ^ k8;
+    return ((k >> 3) * (ROWS / 32) + (cm >> 3)) * 1024u + k8 * 128u + (cc << 4);
+  }
+  uint32_t blk;
+  if (swz == 0) blk = ((((c >> 1) ^ kin) << 1) | (c & 1u));
+  else if (swz == 1) blk = c;
+  else if (swz == 2) blk = c ^ kin;
+  else blk = c ^ (kin << 1);
+  return ((k >> 2) * (ROWS / 32) + (cm >> 3)) * 512u + kin * 128u + (blk << 4);
 }
 
-// byte offset of 16-byte chunk j (0..7) of row r inside a [rows x 128 B] swizzled tile
+// byte offset of 16-byte chunk j (0..7) of row r inside a K-major [rows x 128 B] SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128(uint32_t r, uint32_t j) {
   return (r >> 3) * 1024u + (r & 7u) * 128u + ((j ^ (r & 7u)) << 4);
 }
@@ -437,10 +465,12 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
 #pragma unroll
         for (int ks = 0; ks < kBK / 8; ++ks) {
           // K-major: 8 tf32 = 32 bytes further inside the 128 B row; MN-major: next 8-row k group
-          const uint32_t ka = AL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 1024u;
-          const uint32_t kbo = BL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 1024u;
-          auto da = [&](uint32_t base) { return AL::kKContig ? make_desc(base + ka) : make_desc_mn(base + ka, 4096u); };
-          auto db = [&](uint32_t base) { return BL::kKContig ? make_desc(base + kbo) : make_desc_mn(base + kbo, 4096u); };
+          // K-major: 8 tf32 = 32 B further in the row; MN-major: two 4-row k atoms further
+          const uint32_t ka = AL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (kBM / 32) * 512u;
+          const uint32_t kbo = BL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (BN / 32) * 512u;
+          // (the 8-row-atom experiment has the same per-K-step advance: (ROWS/32) * 1024)
+          auto da = [&](uint32_t base) { return AL::kKContig ? make_desc(base + ka) : make_desc_mn(base + ka, (kBM / 32) * 512u); };
+          auto db = [&](uint32_t base) { return BL::kKContig ? make_desc(base + kbo) : make_desc_mn(base + kbo, (BN / 32) * 512u); };
           const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
           if (PASSES == 3) {
             tc_mma_tf32(tmem_base, da(a_lo), db(b_hi), idesc, first);

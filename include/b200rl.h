@@ -277,6 +277,8 @@ int b200rl_set_gemm_mode(int mode);
 /* Profiling aid: device buffer of int64[64][8] that receives %globaltimer phase stamps of the
  * first 64 CTAs of every tcgen05 GEMM launch (NULL disables). */
 int b200rl_tc_debug_buffer(long long* dev_buf);
+/* Profiling/bring-up aid: selects an MN-major tile layout experiment (0 = production). */
+int b200rl_tc_debug_variant(int v);
 
 /* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
  * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of
