@@ -364,13 +364,17 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
     part[(int64_t)blockIdx.y * N + n] = t;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, float* __restrict__ db,
-                                    int64_t nparts, int64_t N, int beta) {
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part,
+                                                           float* __restrict__ db, int64_t nparts,
+                                                           int64_t N, int beta) {
+  // one warp per column: lanes stride over the partials, fixed-order shuffle reduction
+  const int lane = threadIdx.x & 31;
+  const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (n >= N) return;
   float s = 0.f;
-  for (int64_t p = 0; p < nparts; ++p) s += part[p * N + n];
-  db[n] = beta ? db[n] + s : s;
+  for (int64_t p = lane; p < nparts; p += 32) s += part[p * N + n];
+  s = warp_sum(s);
+  if (lane == 0) db[n] = beta ? db[n] + s : s;
 }
 
 // col2im in gather form (deterministic): dX[n,y,x,c] = sum over kernel taps hitting (y,x).
@@ -455,10 +459,10 @@ static int gemm_mode() {
   return g_gemm_mode;
 }
 
-template <int BN, int STAGES, int PASSES, class AL, class BL>
-static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
+template <int BN, int STAGES, int PASSES, int EPI, class AL, class BL>
+static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
   using L = tc::SmemLayout<BN, STAGES, PASSES>;
-  auto kernel = tc::tc_gemm_kernel<BN, STAGES, PASSES, AL, BL>;
+  auto kernel = tc::tc_gemm_kernel<BN, STAGES, PASSES, EPI, AL, BL>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -472,10 +476,11 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
   const int64_t tm = (g.M + tc::kBM - 1) / tc::kBM, tn = (g.N + BN - 1) / BN;
   const int64_t tiles = tm * tn;
   int splits = 1;
-  if (tiles < kNumSMs && g.K >= 8 * tc::kBK && g.ws != nullptr) {
-    int64_t want = (kNumSMs + tiles - 1) / tiles;
+  const int64_t target = (BN <= 64 ? 2 : 1) * (int64_t)kNumSMs;  // resident CTAs on the chip
+  if (tiles < target && g.K >= 8 * tc::kBK && (g.ws != nullptr || EPI == tc::EPI_COL2IM)) {
+    int64_t want = (target + tiles - 1) / tiles;
     int64_t max_by_k = g.K / (4 * tc::kBK);
-    int64_t max_by_ws = g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t max_by_ws = EPI == tc::EPI_COL2IM ? 65535 : g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
     int64_t s = want < max_by_k ? want : max_by_k;
     if (s > max_by_ws) s = max_by_ws;
     if (s > 65535) s = 65535;
@@ -487,10 +492,10 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
   if (splits < 1) splits = 1;
   B200RL_CHECK_ARG(tm <= 65535, "tc_gemm: M too large for grid.y (%lld tiles)", (long long)tm);
   dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
-  kernel<<<grid, tc::kThreads, L::kBytes, g.st>>>(a, b, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta,
-                                                  splits, kps, (float*)g.ws);
+  kernel<<<grid, tc::kThreads, L::kBytes, g.st>>>(a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act,
+                                                  g.beta, splits, kps, (float*)g.ws);
   B200RL_CHECK_LAUNCH("tc_gemm");
-  if (splits > 1) {
+  if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
     splitk_reduce_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, g.st>>>(
         (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta);
@@ -501,9 +506,10 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g) {
 
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
-  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES>(a, b, g);  // 80 KB -> 2 CTAs / SM
-  if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES>(a, b, g);  // 96 KB -> 2 CTAs / SM
-  return launch_tc_cfg<128, 3, PASSES>(a, b, g);
+  const tc::EpiArgs none{};
+  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 80 KB -> 2 CTAs/SM
+  if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 96 KB -> 2 CTAs/SM
+  return launch_tc_cfg<128, 3, PASSES, tc::EPI_STORE>(a, b, g, none);
 }
 
 template <class AL, class BL>
@@ -512,7 +518,7 @@ static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
   B200RL_CHECK_ARG(g.K > 0, "gemm: K must be > 0");
   B200RL_CHECK_ARG(g.M < (1ll << 31) && g.N < (1ll << 31) && g.K < (1ll << 31), "gemm: dims");
   const int mode = gemm_mode();
-  if (mode != 0 && g.N >= 16 && g.M >= 32) {
+  if (mode != 0 && g.N >= 16 && g.M >= 32 && g.K >= 8) {
     if (mode == 2) return launch_tc<1>(a, b, g);
     return launch_tc<3>(a, b, g);
   }
@@ -536,8 +542,7 @@ static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, vo
   dim3 grid((unsigned)((N + 31) / 32), (unsigned)nparts);
   colsum_partial_kernel<<<grid, 256, 0, st>>>(dZ, (float*)ws, M, N);
   B200RL_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<(unsigned)((N + 127) / 128), 128, 0, st>>>((const float*)ws, db, nparts,
-                                                                   N, beta);
+  colsum_final_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>((const float*)ws, db, nparts, N, beta);
   B200RL_CHECK_LAUNCH("colsum_final");
   return B200RL_OK;
 }
@@ -679,7 +684,20 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     rc = colsum(dY, db, M, F, accumulate, workspace, ws_bytes, st);
     if (rc) return rc;
   }
-  if (dX) {  // dcol[M,K] = dY @ W^T, then gather-form col2im
+  if (dX && gemm_mode() != 0 && (c->C & 3) == 0 && K >= 16 && M >= 32 && F >= 8) {
+    // tcgen05 path: dY @ W^T with the col2im scatter-add fused into the epilogue
+    const int64_t total = (int64_t)c->N * c->H * c->W * c->C;
+    cudaError_t e = cudaMemsetAsync(dX, 0, (size_t)total * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("conv2d_bwd: memset failed: %s", cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+    GemmArgs g{nullptr, nullptr, M, K, F, B200RL_ACT_NONE, 0, nullptr, 0, st};
+    tc::EpiArgs epi{cg, dX};
+    if (gemm_mode() == 2) rc = launch_tc_cfg<128, 3, 1, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
+    else rc = launch_tc_cfg<128, 3, 3, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
+    if (rc) return rc;
+  } else if (dX) {  // dcol[M,K] = dY @ W^T, then gather-form col2im
     const int64_t need = M * K * (int64_t)sizeof(float);
     B200RL_CHECK_ARG(workspace && ws_bytes >= need,
                      "conv2d_bwd: input gradient needs %lld bytes of workspace",

@@ -291,9 +291,23 @@ __device__ __forceinline__ void scatter_tile(unsigned char* hi, unsigned char* l
   }
 }
 
+// Epilogue variants.  EPI_STORE: C (+)= act(acc + bias) or split-K partial.  EPI_COL2IM: the
+// GEMM is dcol[pos, (ky,kx,c)] = dY @ W^T of a convolution input gradient and every 4-channel
+// group is scatter-added straight into dX[n, oy*s+ky, ox*s+kx, c..c+3] with one
+// red.global.add.v4.f32 — the [M, KH*KW*C] dcol matrix is never materialised and split-K
+// partials need no reduction pass (dX must be zeroed by the caller; summation order of the
+// <= KH*KW/s^2 contributions per element is not fixed).
+constexpr int EPI_STORE = 0;
+constexpr int EPI_COL2IM = 1;
+struct EpiArgs {
+  ConvGeom g;
+  float* dx;
+};
+
 // AL / BL are the fp32 operand views of nn.cu (row index = m for A, n for B).
-template <int BN, int STAGES, int PASSES, class AL, class BL>
+template <int BN, int STAGES, int PASSES, int EPI, class AL, class BL>
 __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(const AL a, const BL b,
+                                                           const EpiArgs epi,
                                                            float* __restrict__ C,
                                                            const float* __restrict__ bias,
                                                            int64_t M, int64_t N, int64_t K, int act,
@@ -427,6 +441,29 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       if (m >= M) continue;
       const int64_t nb = n0 + c;
+      if (EPI == EPI_COL2IM) {
+        if (nkb == 0) continue;
+        // pos -> (n, oy, ox); patch index -> (ky, kx*C + c)
+        uint32_t img, rem, oy, ox;
+        epi.g.d_ohow.divmod((uint32_t)m, img, rem);
+        epi.g.d_ow.divmod(rem, oy, ox);
+        const int64_t wc = (int64_t)epi.g.W * epi.g.C;
+        float* base = epi.dx + ((int64_t)img * epi.g.H + (int64_t)oy * epi.g.stride) * wc +
+                      (int64_t)ox * epi.g.stride * epi.g.C;
+#pragma unroll
+        for (int j = 0; j < G; j += 4) {
+          const int64_t kidx = nb + j;
+          if (kidx >= N) break;
+          uint32_t ky, rr;
+          epi.g.d_kwc.divmod((uint32_t)kidx, ky, rr);
+          float* dst = base + (int64_t)ky * wc + rr;
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
+                       "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
+                       "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+                       : "memory");
+        }
+        continue;
+      }
       float v[G];
 #pragma unroll
       for (int j = 0; j < G; ++j) {
