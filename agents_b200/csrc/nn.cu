@@ -53,6 +53,7 @@ struct ARow {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = true;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[m * ld + k]; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return m * ld; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
@@ -64,6 +65,7 @@ struct ACol {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = false;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return m; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
@@ -160,6 +162,7 @@ template <typename T>
 struct AConv {
   ConvView<T> v;
   static constexpr bool kKContig = true;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)m) + v.patch_offset((uint32_t)k));
   }
@@ -173,6 +176,7 @@ template <typename T>
 struct AConvT {
   ConvView<T> v;
   static constexpr bool kKContig = false;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)k) + v.patch_offset((uint32_t)m));
   }
@@ -181,6 +185,37 @@ struct AConvT {
   __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
   __device__ __forceinline__ float ld1(int64_t off) const { return v.load_fast(off); }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return v.load4(off); }
+};
+
+// Raw uint8 pixel views for the tensor-core path: values 0..255 are exact in TF32, the 1/scale of
+// the reference's cast+/255 layer is applied to the accumulator in the epilogue instead.
+struct AConvU8Raw {
+  ConvView<uint8_t> v;
+  static constexpr bool kKContig = true;
+  static constexpr bool kExact = true;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.pos_offset((uint32_t)m); }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return v.patch_offset((uint32_t)k); }
+  __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
+  __device__ __forceinline__ float ld1(int64_t off) const { return (float)v.x[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(v.x + off);
+    return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+  }
+};
+struct AConvTU8Raw {
+  ConvView<uint8_t> v;
+  static constexpr bool kKContig = false;
+  static constexpr bool kExact = true;
+  __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
+  __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.patch_offset((uint32_t)m); }
+  __device__ __forceinline__ int64_t k_off(int64_t k) const { return v.pos_offset((uint32_t)k); }
+  __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
+  __device__ __forceinline__ float ld1(int64_t off) const { return (float)v.x[off]; }
+  __device__ __forceinline__ float4 ld4(int64_t off) const {
+    const uchar4 u = *reinterpret_cast<const uchar4*>(v.x + off);
+    return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
+  }
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -413,6 +448,7 @@ struct GemmArgs {
   void* ws;
   int64_t ws_bytes;
   cudaStream_t st;
+  float out_scale = 1.f;  // tensor-core path only: multiplies the accumulator (raw-u8 operands)
 };
 
 template <int BM, int BN, int TM, int TN, class AL, class BL>
@@ -461,7 +497,7 @@ static int gemm_mode() {
 
 template <int BN, int STAGES, int PASSES, int EPI, class AL, class BL>
 static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
-  using L = tc::SmemLayout<BN, STAGES, PASSES>;
+  using L = tc::SmemLayout<BN, STAGES, PASSES, AL::kExact>;
   auto kernel = tc::tc_gemm_kernel<BN, STAGES, PASSES, EPI, AL, BL>;
   static bool configured = false;
   if (!configured) {
@@ -493,7 +529,7 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
   B200RL_CHECK_ARG(tm <= 65535, "tc_gemm: M too large for grid.y (%lld tiles)", (long long)tm);
   dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
   kernel<<<grid, tc::kThreads, L::kBytes, g.st>>>(a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act,
-                                                  g.beta, splits, kps, (float*)g.ws);
+                                                  g.beta, splits, kps, (float*)g.ws, g.out_scale);
   B200RL_CHECK_LAUNCH("tc_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
@@ -507,7 +543,7 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
   const tc::EpiArgs none{};
-  if (g.N <= 32) return launch_tc_cfg<32, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 80 KB -> 2 CTAs/SM
+  if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), PASSES, tc::EPI_STORE>(a, b, g, none);  // <= 96 KB -> 2 CTAs/SM
   if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 96 KB -> 2 CTAs/SM
   return launch_tc_cfg<128, 3, PASSES, tc::EPI_STORE>(a, b, g, none);
 }
@@ -650,6 +686,11 @@ int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt
   const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
   GemmArgs g{Y, bias, M, c->F, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
   if (x_is_u8) {
+    if (gemm_mode() == 1 && c->F >= 16 && M >= 32 && K >= 8) {   // raw pixels, 2-pass 3xTF32
+      g.out_scale = 1.f / x_scale;
+      AConvU8Raw a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
+      return launch_tc<3>(a, BRow{Wt, c->F}, g);
+    }
     AConv<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
     return launch_gemm(a, BRow{Wt, c->F}, g);
   }
@@ -671,7 +712,11 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
   const int64_t F = c->F;
   {  // dW[K,F] = im2col(X)^T @ dY
     GemmArgs g{dW, nullptr, K, F, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
-    if (x_is_u8) {
+    if (x_is_u8 && gemm_mode() == 1 && F >= 16 && K >= 32 && M >= 8) {
+      g.out_scale = 1.f / x_scale;
+      AConvTU8Raw a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
+      rc = launch_tc<3>(a, BRow{dY, F}, g);
+    } else if (x_is_u8) {
       AConvT<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
       rc = launch_gemm(a, BRow{dY, F}, g);
     } else {

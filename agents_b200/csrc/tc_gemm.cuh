@@ -166,12 +166,15 @@ __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned cha
   }
 }
 
-template <int BN, int STAGES, int PASSES>
+// A_EXACT: the A view yields values that are exactly representable in TF32 (raw uint8 pixels), so
+// A needs no "lo" plane and the product needs only 2 passes (a*b_lo + a*b_hi).
+template <int BN, int STAGES, int PASSES, bool A_EXACT = false>
 struct SmemLayout {
   static constexpr int kATile = kBM * 128;
   static constexpr int kBTile = BN * 128;
-  static constexpr int kNumA = PASSES == 3 ? 2 : 1;
-  static constexpr int kStage = kNumA * (kATile + kBTile);
+  static constexpr int kNumA = (PASSES == 3 && !A_EXACT) ? 2 : 1;   // A planes
+  static constexpr int kNumB = PASSES == 3 ? 2 : 1;                 // B planes
+  static constexpr int kStage = kNumA * kATile + kNumB * kBTile;
   static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
 };
 
@@ -313,8 +316,9 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
                                                            int64_t M, int64_t N, int64_t K, int act,
                                                            int beta, int splits,
                                                            int64_t k_per_split,
-                                                           float* __restrict__ ws) {
-  using L = SmemLayout<BN, STAGES, PASSES>;
+                                                           float* __restrict__ ws,
+                                                           float out_scale) {
+  using L = SmemLayout<BN, STAGES, PASSES, AL::kExact>;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -356,6 +360,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
   if (warp < 8) {
     // ===================== producers =====================
     constexpr bool kLo = PASSES == 3;
+    constexpr bool kLoA = PASSES == 3 && !AL::kExact;
     constexpr int NRA = AL::kKContig ? kBM * 8 / kProducerThreads : 1;
     constexpr int NRB = BL::kKContig ? BN * 8 / kProducerThreads : 1;
     static_assert(BN * 8 >= kProducerThreads, "BN must be >= 32");
@@ -404,8 +409,8 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       unsigned char* a_lo = st + L::kATile;
       unsigned char* b_hi = st + L::kNumA * L::kATile;
       unsigned char* b_lo = b_hi + L::kBTile;
-      if (AL::kKContig) scatter_tile<kBM, kLo, true>(a_hi, a_lo, tid, av);
-      else scatter_tile_mn<kBM, kLo>(a_hi, a_lo, tid, av);
+      if (AL::kKContig) scatter_tile<kBM, kLoA, true>(a_hi, a_lo, tid, av);
+      else scatter_tile_mn<kBM, kLoA>(a_hi, a_lo, tid, av);
       if (BL::kKContig) scatter_tile<BN, kLo, true>(b_hi, b_lo, tid, bv);
       else scatter_tile_mn<BN, kLo>(b_hi, b_lo, tid, bv);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -467,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       float v[G];
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        float x = nkb > 0 ? __uint_as_float(r[j]) : 0.f;
+        float x = nkb > 0 ? __uint_as_float(r[j]) * out_scale : 0.f;
         if (splits == 1 && nb + j < N) {
           if (bias) x += bias[nb + j];
           x = apply_act(x, act);
@@ -509,7 +514,10 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
           auto da = [&](uint32_t base) { return AL::kKContig ? make_desc(base + ka) : make_desc_mn(base + ka, (kBM / 32) * 512u); };
           auto db = [&](uint32_t base) { return BL::kKContig ? make_desc(base + kbo) : make_desc_mn(base + kbo, (BN / 32) * 512u); };
           const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
-          if (PASSES == 3) {
+          if (PASSES == 3 && AL::kExact) {
+            tc_mma_tf32(tmem_base, da(a_hi), db(b_lo), idesc, first);
+            tc_mma_tf32(tmem_base, da(a_hi), db(b_hi), idesc, 1u);
+          } else if (PASSES == 3) {
             tc_mma_tf32(tmem_base, da(a_lo), db(b_hi), idesc, first);
             tc_mma_tf32(tmem_base, da(a_hi), db(b_lo), idesc, 1u);
             tc_mma_tf32(tmem_base, da(a_hi), db(b_hi), idesc, 1u);
