@@ -16,6 +16,8 @@ both evaluations are identical, so it is evaluated once here.
 """
 import collections
 
+import os
+
 import torch
 
 from agents_b200 import _lib
@@ -104,6 +106,8 @@ class DqnAgent(tf_agent.TFAgent):
         train_step_counter=train_step_counter, training_data_spec=training_data_spec,
         device=device)
     self._nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
+    self._overlap_target = os.environ.get('B200RL_DQN_OVERLAP', '1') != '0'
+    self._side_stream = torch.cuda.Stream(device=device) if self._overlap_target else None
     self._clip_offsets = None
     self.replicas = 1           # set by train.Learner for data-parallel runs
     self._grad_sync = None      # callable(flat_grads) installed by train.Learner
@@ -164,14 +168,23 @@ class DqnAgent(tf_agent.TFAgent):
     B, T = exp.discount.shape[0], exp.discount.shape[1]
     obs0, _ = self._split_obs(nest.map_structure(lambda t: t[:, 0], exp.observation))
     obsn, next_mask = self._split_obs(nest.map_structure(lambda t: t[:, T - 1], exp.observation))
+    # The target-side forwards do not depend on the online forward: fork them onto a side
+    # stream (also inside a captured graph) and join before the TD kernel.
+    main = torch.cuda.current_stream()
+    side = self._side_stream if self._overlap_target else None
+    if side is not None:
+      side.wait_stream(main)
+    with torch.cuda.stream(side if side is not None else main):
+      next_t, _ = self._target_q_network(obsn)
+      next_sel = next_t
+      if self._DOUBLE_Q:
+        next_sel, _ = self._q_network(obsn)        # DdqnAgent (dqn_agent.py:686-688)
     if keep_tape:
       q, tape = self._q_network.forward_train(obs0)
     else:
       (q, _), tape = self._q_network(obs0), None
-    next_t, _ = self._target_q_network(obsn)
-    next_sel = next_t
-    if self._DOUBLE_Q:
-      next_sel, _ = self._q_network(obsn)          # DdqnAgent (dqn_agent.py:686-688)
+    if side is not None:
+      main.wait_stream(side)
     dev = q.device
     actions = exp.action[:, 0].to(torch.int32).contiguous()
     step0 = exp.step_type[:, 0].to(torch.int32).contiguous()

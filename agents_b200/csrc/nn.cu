@@ -513,10 +513,10 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
   const int64_t tiles = tm * tn;
   int splits = 1;
   const int64_t target = (BN <= 64 ? 2 : 1) * (int64_t)kNumSMs;  // resident CTAs on the chip
-  if (tiles < target && g.K >= 8 * tc::kBK && (g.ws != nullptr || EPI == tc::EPI_COL2IM)) {
-    int64_t want = (target + tiles - 1) / tiles;
+  if (tiles < target && g.K >= 8 * tc::kBK && (g.ws != nullptr || EPI != tc::EPI_STORE)) {
+    int64_t want = target / tiles;  // only split when a whole extra set of CTAs fits on the chip
     int64_t max_by_k = g.K / (4 * tc::kBK);
-    int64_t max_by_ws = EPI == tc::EPI_COL2IM ? 65535 : g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t max_by_ws = EPI != tc::EPI_STORE ? 65535 : g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
     int64_t s = want < max_by_k ? want : max_by_k;
     if (s > max_by_ws) s = max_by_ws;
     if (s > 65535) s = 65535;
@@ -548,6 +548,12 @@ static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
   return launch_tc_cfg<128, 3, PASSES, tc::EPI_STORE>(a, b, g, none);
 }
 
+// Weight-gradient GEMMs (no bias / activation): in tensor-core mode the split-K partials are
+// accumulated with red.global.add straight into the (zeroed) gradient instead of going through
+// a workspace + reduce kernel.  Summation order across splits is not fixed.
+template <class AL, class BL>
+static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g);
+
 template <class AL, class BL>
 static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
   if (g.M <= 0 || g.N <= 0) return B200RL_OK;
@@ -566,6 +572,29 @@ static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
   const int64_t t128 = ((g.M + 127) / 128) * ((g.N + 127) / 128);
   if (t128 >= kNumSMs) return launch_gemm_cfg<128, 128, 8, 8>(a, b, g);
   return launch_gemm_cfg<64, 64, 4, 4>(a, b, g);
+}
+
+template <class AL, class BL>
+static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g) {
+  const int mode = gemm_mode();
+  if (mode == 0 || g.N < 16 || g.M < 32 || g.K < 8 || g.bias != nullptr || g.act != B200RL_ACT_NONE)
+    return launch_gemm(a, b, g);
+  if (!g.beta) {
+    cudaError_t e = cudaMemsetAsync(g.C, 0, (size_t)(g.M * g.N) * sizeof(float), g.st);
+    if (e != cudaSuccess) {
+      set_error("grad gemm: memset failed: %s", cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+  }
+  const tc::EpiArgs none{};
+  if (mode == 2) {
+    if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), 1, tc::EPI_ATOMIC>(a, b, g, none);
+    if (g.N <= 64) return launch_tc_cfg<64, 2, 1, tc::EPI_ATOMIC>(a, b, g, none);
+    return launch_tc_cfg<128, 3, 1, tc::EPI_ATOMIC>(a, b, g, none);
+  }
+  if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), 3, tc::EPI_ATOMIC>(a, b, g, none);
+  if (g.N <= 64) return launch_tc_cfg<64, 2, 3, tc::EPI_ATOMIC>(a, b, g, none);
+  return launch_tc_cfg<128, 3, 3, tc::EPI_ATOMIC>(a, b, g, none);
 }
 
 static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, void* ws,
@@ -657,7 +686,7 @@ int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* d
   }
   if (dW) {
     GemmArgs g{dW, nullptr, K, N, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
-    rc = launch_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g);
+    rc = launch_grad_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g);
     if (rc) return rc;
   }
   if (db) {
@@ -715,13 +744,13 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     if (x_is_u8 && gemm_mode() == 1 && F >= 16 && K >= 32 && M >= 8) {
       g.out_scale = 1.f / x_scale;
       AConvTU8Raw a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
-      rc = launch_tc<3>(a, BRow{dY, F}, g);
+      rc = launch_grad_gemm(a, BRow{dY, F}, g);
     } else if (x_is_u8) {
       AConvT<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
       rc = launch_gemm(a, BRow{dY, F}, g);
     } else {
       AConvT<float> a{ConvView<float>{(const float*)X, cg, 1.f}};
-      rc = launch_gemm(a, BRow{dY, F}, g);
+      rc = launch_grad_gemm(a, BRow{dY, F}, g);
     }
     if (rc) return rc;
   }

@@ -302,6 +302,7 @@ __device__ __forceinline__ void scatter_tile(unsigned char* hi, unsigned char* l
 // <= KH*KW/s^2 contributions per element is not fixed).
 constexpr int EPI_STORE = 0;
 constexpr int EPI_COL2IM = 1;
+constexpr int EPI_ATOMIC = 2;  // C += acc with red.global.add (split-K without a reduce pass; C pre-zeroed)
 struct EpiArgs {
   ConvGeom g;
   float* dx;
@@ -466,6 +467,23 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
                        "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
                        "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
                        : "memory");
+        }
+        continue;
+      }
+      if (EPI == EPI_ATOMIC) {
+        if (nkb == 0) continue;
+        float* dst = C + m * N + nb;
+        if ((N & 3) == 0 && nb + G - 1 < N) {
+#pragma unroll
+          for (int j = 0; j < G; j += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                         "f"(__uint_as_float(r[j]) * out_scale), "f"(__uint_as_float(r[j + 1]) * out_scale),
+                         "f"(__uint_as_float(r[j + 2]) * out_scale), "f"(__uint_as_float(r[j + 3]) * out_scale)
+                         : "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < G; ++j)
+            if (nb + j < N) atomicAdd(dst + j, __uint_as_float(r[j]) * out_scale);
         }
         continue;
       }

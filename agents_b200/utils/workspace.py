@@ -1,4 +1,4 @@
-"""Per-device scratch buffer handed to libb200rl (split-K partials, dcol, norm partials).
+"""Per-(device, stream) scratch buffer handed to libb200rl (split-K partials, dcol, norm partials).
 
 Grows on demand; growth during CUDA-graph capture is an error (warm up eagerly first, as
 `utils.common.function` does).
@@ -12,7 +12,9 @@ _MIN_BYTES = 8 << 20
 def get(device, nbytes=0):
   """Returns (tensor, nbytes) of a uint8 scratch buffer of at least `nbytes` on `device`."""
   device = torch.device(device)
-  key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+  index = device.index if device.index is not None else torch.cuda.current_device()
+  # one buffer per stream: kernels on concurrent streams must not share split-K partials
+  key = (device.type, index, torch.cuda.current_stream(index).cuda_stream)
   cur = _WS.get(key)
   need = max(int(nbytes), _MIN_BYTES)
   if cur is None or cur.numel() < need:
