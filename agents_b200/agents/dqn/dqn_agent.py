@@ -27,6 +27,7 @@ from agents_b200.trajectories import time_step as ts
 from agents_b200.trajectories import trajectory
 from agents_b200.utils import common
 from agents_b200.utils import nest
+from agents_b200.utils import workspace
 
 
 class DqnLossInfo(collections.namedtuple('DqnLossInfo', ('td_loss', 'td_error'))):
@@ -106,7 +107,8 @@ class DqnAgent(tf_agent.TFAgent):
         train_step_counter=train_step_counter, training_data_spec=training_data_spec,
         device=device)
     self._nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
-    self._overlap_target = os.environ.get('B200RL_DQN_OVERLAP', '1') != '0'
+    # 0 = never, 1 = inside common.function graphs (default), 2 = always
+    self._overlap_target = int(os.environ.get('B200RL_DQN_OVERLAP', '1'))
     self._side_stream = torch.cuda.Stream(device=device) if self._overlap_target else None
     self._clip_offsets = None
     self.replicas = 1           # set by train.Learner for data-parallel runs
@@ -171,10 +173,15 @@ class DqnAgent(tf_agent.TFAgent):
     # The target-side forwards do not depend on the online forward: fork them onto a side
     # stream (also inside a captured graph) and join before the TD kernel.
     main = torch.cuda.current_stream()
-    side = self._side_stream if self._overlap_target else None
+    side = None
+    if self._overlap_target == 2 or (self._overlap_target and
+                                     torch.cuda.is_current_stream_capturing()):
+      # eager launches are host-bound, the fork only pays inside a captured graph
+      side = self._side_stream
     if side is not None:
       side.wait_stream(main)
-    with torch.cuda.stream(side if side is not None else main):
+    with torch.cuda.stream(side if side is not None else main), \
+        workspace.slot(1 if side is not None else 0):
       next_t, _ = self._target_q_network(obsn)
       next_sel = next_t
       if self._DOUBLE_Q:
@@ -185,6 +192,8 @@ class DqnAgent(tf_agent.TFAgent):
       (q, _), tape = self._q_network(obs0), None
     if side is not None:
       main.wait_stream(side)
+    elif self._overlap_target and not torch.cuda.is_current_stream_capturing():
+      workspace.mirror(q.device, 1)   # size the side-stream scratch for a later capture
     dev = q.device
     actions = exp.action[:, 0].to(torch.int32).contiguous()
     step0 = exp.step_type[:, 0].to(torch.int32).contiguous()

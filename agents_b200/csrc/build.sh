@@ -10,7 +10,11 @@ FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompil
 pids=()
 for f in "$here"/*.cu; do
   o="$here/obj/$(basename "${f%.cu}").o"
-  if [[ ! -f "$o" || "$f" -nt "$o" || "$here/common.cuh" -nt "$o" || "$here/../../include/b200rl.h" -nt "$o" ]]; then
+  stale=0
+  for dep in "$f" "$here"/*.cuh "$here/../../include/b200rl.h"; do
+    [[ ! -f "$o" || "$dep" -nt "$o" ]] && stale=1
+  done
+  if [[ $stale -eq 1 ]]; then
     "$NVCC" "${FLAGS[@]}" -c "$f" -o "$o" > "$o.log" 2>&1 &
     pids+=($!)
   fi

@@ -36,7 +36,14 @@ constexpr int kThreads = 288;
 
 // optional phase stamps (b200rl_tc_debug_buffer): [block][8] nanosecond timers
 __device__ long long* g_tc_dbg = nullptr;
-__device__ int g_tc_variant = 0;  // layout experiments for MN-major tiles (profiles/tc_layout_probe.py)
+// Pipeline ablations (profiles/tc_ablate.py) are compiled in only with -DB200RL_TC_ABLATE; the
+// production library ignores b200rl_tc_debug_variant.
+__device__ int g_tc_variant = 0;
+#ifdef B200RL_TC_ABLATE
+#define TC_ABL(v) (v)
+#else
+#define TC_ABL(v) 0
+#endif
 __device__ __forceinline__ long long gtimer() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -58,8 +65,8 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-// Non-blocking poll: mbarrier.try_wait may suspend the thread for a system-dependent time and
-// measured ~65 us per wait on barriers completed by tcgen05.commit (profiles/README.md, r1 v0).
+// Non-blocking test_wait poll (the blocking try_wait form faulted in this kernel on the r1 pool,
+// see profiles/README.md; polling by one lane per warp measured the same as polling by all).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done;
   do {
@@ -108,15 +115,7 @@ __device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr, uint32_t sbo_by
   d |= (uint64_t)(512 >> 4) << 16;                 // LBO: next 32-row M/N group (adjacent atom)
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;  // SBO: next 4-row k atom = (ROWS/32) atoms
   d |= (uint64_t)1 << 46;                          // version = 1 (sm_100)
-  const int var = g_tc_variant;
-  const uint64_t lt = (var & 1) ? ((var & 16) ? 0ull : 2ull) : 1ull;
-  d |= lt << 61;                                   // layout type (1 = SWIZZLE_128B_BASE32B)
-  if (var & 8) {                                   // 8-row atoms: LBO 1024, SBO = G * 1024
-    d &= ~((uint64_t)0x3FFF << 16);
-    d |= (uint64_t)(1024 >> 4) << 16;
-    d &= ~((uint64_t)0x3FFF << 32);
-    d |= (uint64_t)(((sbo_bytes * 2) >> 4) & 0x3FFF) << 32;
-  }
+  d |= (uint64_t)1 << 61;                          // layout type 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 __host__ __device__ constexpr uint32_t make_idesc(int bn, bool a_mn, bool b_mn) {
@@ -130,19 +129,7 @@ template <int ROWS>
 __device__ __forceinline__ uint32_t mn128(uint32_t cm, uint32_t k) {
   // atoms are tiled M/N-fastest (the arrangement cute's tile_to_shape produces)
   const uint32_t c = cm & 7u, kin = k & 3u;
-  const int var = g_tc_variant;
-  const int swz = (var >> 1) & 3;
-  if (var & 8) {  // SW128 (8-row atoms) arrangement: atoms of 8 k rows, M/N-fastest
-    const uint32_t k8 = k & 7u;
-    uint32_t cc = c;
-    if (swz == 2) cc = c ^ k8;
-    return ((k >> 3) * (ROWS / 32) + (cm >> 3)) * 1024u + k8 * 128u + (cc << 4);
-  }
-  uint32_t blk;
-  if (swz == 0) blk = ((((c >> 1) ^ kin) << 1) | (c & 1u));
-  else if (swz == 1) blk = c;
-  else if (swz == 2) blk = c ^ kin;
-  else blk = c ^ (kin << 1);
+  const uint32_t blk = (((c >> 1) ^ kin) << 1) | (c & 1u);   // 32-byte block XOR k, 16 B half kept
   return ((k >> 2) * (ROWS / 32) + (cm >> 3)) * 512u + kin * 128u + (blk << 4);
 }
 
@@ -159,10 +146,15 @@ __device__ __forceinline__ void split_store(unsigned char* hi_tile, unsigned cha
   h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
   h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u);
   h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
-  *reinterpret_cast<float4*>(hi_tile + off) = h;
+  // explicit st.shared: the tile pointers come from integer alignment arithmetic, which makes
+  // the compiler fall back to generic ST.E otherwise
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr(hi_tile) + off),
+               "f"(h.x), "f"(h.y), "f"(h.z), "f"(h.w)
+               : "memory");
   if (WITH_LO) {
-    float4 l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-    *reinterpret_cast<float4*>(lo_tile + off) = l;
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(smem_addr(lo_tile) + off),
+                 "f"(v.x - h.x), "f"(v.y - h.y), "f"(v.z - h.z), "f"(v.w - h.w)
+                 : "memory");
   }
 }
 
@@ -175,7 +167,7 @@ struct SmemLayout {
   static constexpr int kNumA = (PASSES == 3 && !A_EXACT) ? 2 : 1;   // A planes
   static constexpr int kNumB = PASSES == 3 ? 2 : 1;                 // B planes
   static constexpr int kStage = kNumA * kATile + kNumB * kBTile;
-  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/;
+  static constexpr int kBytes = STAGES * kStage + 1024 /*alignment slack*/ + 256 /*barriers*/ + BN * 4 /*bias*/;
 };
 
 // One chunk = 4 consecutive k of one row.  roff = view.row_off(row); koff[i] = view.k_off(k+i).
@@ -392,38 +384,57 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       if (BL::kKContig) gather_tile<BN>(b, b_off, b_ok, k0, ke, b_vec, tid, dst);
       else gather_tile_mn<BN>(b, n0, N, k0, ke, b_vec, tid, dst);
     };
+    const int abl = TC_ABL(g_tc_variant);   // ablation probes (profiles/tc_ablate.py); 0 in production
     if (nkb > 0) {
       gather_a(kb, av);
       gather_b(kb, bv);
     }
-    for (int kbi = 0; kbi < nkb; ++kbi) {
+    // One K block: issue the NEXT block's global loads into `nxt`, then split/store `cur`.
+    // The two register sets swap roles every block (loop unrolled by two below) — copying
+    // nxt -> cur at the end of the body would wait for the loads that were just issued.
+    auto k_block = [&](int kbi, float4 (&cur_a)[NVA], float4 (&cur_b)[NVB], float4 (&nxt_a)[NVA],
+                       float4 (&nxt_b)[NVB]) {
       const int s = kbi % STAGES;
       const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
-      if (kbi + 1 < nkb) {  // issue the next block's global loads before touching shared memory
+      if (kbi + 1 < nkb && abl != 22 && abl != 23 && abl != 24) {
         const int64_t k1 = kb + (int64_t)(kbi + 1) * kBK;
-        gather_a(k1, an);
-        gather_b(k1, bn);
+        gather_a(k1, nxt_a);
+        gather_b(k1, nxt_b);
       }
       if (kbi >= STAGES) mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
+      if (abl == 20 || abl == 23 || abl == 24) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&full[s]));
+        return;
+      }
       unsigned char* st = smem + s * L::kStage;
       unsigned char* a_hi = st;
       unsigned char* a_lo = st + L::kATile;
       unsigned char* b_hi = st + L::kNumA * L::kATile;
       unsigned char* b_lo = b_hi + L::kBTile;
-      if (AL::kKContig) scatter_tile<kBM, kLoA, true>(a_hi, a_lo, tid, av);
-      else scatter_tile_mn<kBM, kLoA>(a_hi, a_lo, tid, av);
-      if (BL::kKContig) scatter_tile<BN, kLo, true>(b_hi, b_lo, tid, bv);
-      else scatter_tile_mn<BN, kLo>(b_hi, b_lo, tid, bv);
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      if (AL::kKContig) scatter_tile<kBM, kLoA, true>(a_hi, a_lo, tid, cur_a);
+      else scatter_tile_mn<kBM, kLoA>(a_hi, a_lo, tid, cur_a);
+      if (BL::kKContig) scatter_tile<BN, kLo, true>(b_hi, b_lo, tid, cur_b);
+      else scatter_tile_mn<BN, kLo>(b_hi, b_lo, tid, cur_b);
+      // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
+      // MEMBAR would wait for the next block's global loads that are deliberately in flight.
+      // The release-arrive below orders the stores; the MMA thread runs the proxy fence after
+      // its acquire-wait, i.e. on the causality path between these stores and tcgen05.mma.
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&full[s]));
-#pragma unroll
-      for (int i = 0; i < NVA; ++i) av[i] = an[i];
-#pragma unroll
-      for (int i = 0; i < NVB; ++i) bv[i] = bn[i];
+    };
+    for (int kbi = 0; kbi < nkb; kbi += 2) {
+      k_block(kbi, av, bv, an, bn);
+      if (kbi + 1 < nkb) k_block(kbi + 1, an, bn, av, bv);
     }
     // ===================== epilogue =====================
     if (tid == 0) stamp(2);
+    // bias slice of this tile -> shared memory while the last MMAs drain
+    float* sbias = reinterpret_cast<float*>(bars + 256);
+    if (EPI == EPI_STORE) {
+      if (tid < BN) sbias[tid] = (bias != nullptr && n0 + tid < N) ? bias[n0 + tid] : 0.f;
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
     mbar_wait(smem_addr(accum), 0u);
     if (tid == 0) stamp(4);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -432,20 +443,28 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
     float* out = (splits > 1) ? ws + (int64_t)split * M * N : C;
     const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
     constexpr int G = 16;  // columns fetched per tcgen05.ld
+    constexpr int kStagePitch = BN + 4;
+    static_assert(kBM * (BN + 4) * 4 <= STAGES * L::kStage, "epilogue staging tile must fit");
+    // all TMEM loads of this warp's column half are issued before the single wait
+    uint32_t racc[BN / 2];
 #pragma unroll
     for (int cc = 0; cc < BN / 2; cc += G) {
-      const int c = half * (BN / 2) + cc;
-      uint32_t r[G];
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(half * (BN / 2) + cc);
       asm volatile(
           "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
           "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-            "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-            "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+          : "=r"(racc[cc + 0]), "=r"(racc[cc + 1]), "=r"(racc[cc + 2]), "=r"(racc[cc + 3]),
+            "=r"(racc[cc + 4]), "=r"(racc[cc + 5]), "=r"(racc[cc + 6]), "=r"(racc[cc + 7]),
+            "=r"(racc[cc + 8]), "=r"(racc[cc + 9]), "=r"(racc[cc + 10]), "=r"(racc[cc + 11]),
+            "=r"(racc[cc + 12]), "=r"(racc[cc + 13]), "=r"(racc[cc + 14]), "=r"(racc[cc + 15])
           : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (m >= M) continue;
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int cc = 0; cc < BN / 2; cc += G) {
+      const int c = half * (BN / 2) + cc;
+      const uint32_t* r = racc + cc;
+      if (m >= M && !(EPI == EPI_STORE && vec_out)) continue;
       const int64_t nb = n0 + c;
       if (EPI == EPI_COL2IM) {
         if (nkb == 0) continue;
@@ -491,21 +510,40 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         float x = nkb > 0 ? __uint_as_float(r[j]) * out_scale : 0.f;
-        if (splits == 1 && nb + j < N) {
-          if (bias) x += bias[nb + j];
+        if (splits == 1 && nb + j < N && m < M) {
+          x += sbias[c + j];
           x = apply_act(x, act);
           if (beta) x += out[m * N + nb + j];
         }
         v[j] = x;
       }
-      if (vec_out && nb + G - 1 < N) {
-        float4* dst = reinterpret_cast<float4*>(out + m * N + nb);
+      if (vec_out) {
+        // stage the tile in the (now idle) operand buffers so that global rows are written by
+        // adjacent lanes; row pitch BN+4 floats keeps the 16-byte stores conflict-free
+        float* srow = reinterpret_cast<float*>(smem) + (q * 32 + lane) * kStagePitch + c;
 #pragma unroll
-        for (int j = 0; j < G / 4; ++j) dst[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        for (int j = 0; j < G; j += 4)
+          *reinterpret_cast<float4*>(srow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       } else {
 #pragma unroll
         for (int j = 0; j < G; ++j)
           if (nb + j < N) out[m * N + nb + j] = v[j];
+      }
+    }
+    if (EPI == EPI_STORE && vec_out) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 epilogue warps only
+      constexpr int LPR = BN / 4;                        // lanes per tile row
+      constexpr int RPI = 32 / LPR;                      // rows per store instruction
+      const int col = (lane % LPR) * 4;
+#pragma unroll 4
+      for (int rr = 0; rr < 16; rr += RPI) {
+        const int row = warp * 16 + rr + lane / LPR;
+        const int64_t gm = m0 + row;
+        if (gm < M && n0 + col < N) {
+          const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) +
+                                                            row * kStagePitch + col);
+          *reinterpret_cast<float4*>(out + gm * N + n0 + col) = t;
+        }
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -518,6 +556,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
         const int s = kbi % STAGES;
         const uint32_t ph = (uint32_t)((kbi / STAGES) & 1);
         mbar_wait(smem_addr(&full[s]), ph);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         unsigned char* st = smem + s * L::kStage;
         const uint32_t a_hi = smem_addr(st), a_lo = a_hi + L::kATile;
@@ -532,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
           auto da = [&](uint32_t base) { return AL::kKContig ? make_desc(base + ka) : make_desc_mn(base + ka, (kBM / 32) * 512u); };
           auto db = [&](uint32_t base) { return BL::kKContig ? make_desc(base + kbo) : make_desc_mn(base + kbo, (BN / 32) * 512u); };
           const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
+          if ((TC_ABL(g_tc_variant) == 21 || TC_ABL(g_tc_variant) == 24) && !(kbi == 0 && ks == 0)) continue;
           if (PASSES == 3 && AL::kExact) {
             tc_mma_tf32(tmem_base, da(a_hi), db(b_lo), idesc, first);
             tc_mma_tf32(tmem_base, da(a_hi), db(b_hi), idesc, 1u);
