@@ -55,7 +55,9 @@ class _GraphFunction(object):
       self._graph = torch.cuda.CUDAGraph()
       _CAPTURE_EFFECTS = []
       try:
-        with torch.cuda.graph(self._graph):
+        # thread_local: other threads (the NCCL watchdog polling its events, a data-loader
+        # thread) may keep calling CUDA while this thread captures
+        with torch.cuda.graph(self._graph, capture_error_mode='thread_local'):
           self._out = self._fn(*s_args, **s_kwargs)
       finally:
         self._effects, _CAPTURE_EFFECTS = _CAPTURE_EFFECTS, None

@@ -286,18 +286,26 @@ def main():
 
   use_graph = not args.no_graph
   fn = common.function(step, warmup=1) if use_graph else step
+  fn()                                   # eager warm-up call (sizes workspaces)
+  ok = 1
   try:
-    for _ in range(W + 2):
-      fn()
-  except Exception as e:  # e.g. a collective that cannot be captured on this stack -> eager
+    fn()                                 # capture + first replay
+  except Exception as e:  # a step that cannot be captured on this stack -> eager
     if not use_graph:
       raise
-    sys.stderr.write(f'CUDA-graph capture failed ({type(e).__name__}: {e}); running eagerly\n')
+    sys.stderr.write(f'[rank {rank}] CUDA-graph capture failed ({type(e).__name__}: {e})\n')
+    ok = 0
+    torch.cuda.synchronize()
+    step()                               # keeps the collective count equal to a successful rank's
+  if world > 1 and use_graph:            # all ranks must agree on graph vs eager
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = int(flag.item())
+  if use_graph and not ok:
     use_graph = False
     fn = step
-    torch.cuda.synchronize()
-    for _ in range(W):
-      fn()
+  for _ in range(W):
+    fn()
   sync_all()
 
   # ---- timed region: K steps, CUDA events, max over ranks ---------------------------------------
@@ -347,7 +355,7 @@ def main():
   n_u = max(10, min(K, 50))
   ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   # the update alone, replayed from its own graph so that the events bracket GPU time
-  train_only = common.function(lambda: agent.train(exp), warmup=1) if use_graph else (
+  train_only = common.function(lambda: agent.train(exp), warmup=1) if (use_graph and world == 1) else (
       lambda: agent.train(exp))
   for _ in range(3):
     train_only()

@@ -54,15 +54,24 @@ def main():
       torch.ones(B, T, dtype=torch.int32, device=dev), r(B, T), torch.ones(B, T, device=dev))
   use_graph = os.environ.get('PPO_BENCH_GRAPH', '1') == '1'
   fn = common.function(agent.train, warmup=1) if use_graph else agent.train
+  fn(exp)                                  # eager warm-up
+  ok = 1
   try:
-    for _ in range(3):
-      fn(exp)
+    fn(exp)                                # capture + first replay
   except Exception as e:
     if not use_graph:
       raise
-    sys.stderr.write(f'graph capture failed ({e}); eager\n')
+    sys.stderr.write(f'[rank {strategy.rank}] graph capture failed ({e}); eager\n')
+    ok = 0
+    torch.cuda.synchronize()
+    agent.train(exp)                       # same number of collectives as a successful rank
+  if world > 1 and use_graph:
+    flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = int(flag.item())
+  if use_graph and not ok:
     use_graph, fn = False, agent.train
-    fn(exp)
+  fn(exp)
   torch.cuda.synchronize()
   if world > 1:
     dist.barrier()
