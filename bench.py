@@ -460,7 +460,13 @@ def main():
       line['cpu_baseline'] = cpu
     print(json.dumps(line), flush=True)
   if world > 1:
-    dist.destroy_process_group()
+    # CUDA graphs that captured NCCL kernels make the communicator teardown hang on this stack:
+    # leave without running destructors once every rank is done.
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':

@@ -94,7 +94,13 @@ def main():
                           samples_per_s=B_total * T * epochs / (ms * 1e-3), cuda_graph=use_graph,
                           loss=float(info.loss.item()), scaling='strong')), flush=True)
   if world > 1:
-    dist.destroy_process_group()
+    # CUDA graphs that captured NCCL kernels make the communicator teardown hang on this stack:
+    # leave without running destructors once every rank is done.
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 if __name__ == '__main__':
