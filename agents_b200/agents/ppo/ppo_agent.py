@@ -22,6 +22,7 @@ from agents_b200 import _lib
 from agents_b200.agents import tf_agent
 from agents_b200.agents.ppo import ppo_policy
 from agents_b200.networks import network as network_lib
+from agents_b200.specs import tensor_spec
 from agents_b200.trajectories import trajectory
 from agents_b200.utils import nest
 from agents_b200.utils import tensor_normalizer
@@ -57,8 +58,6 @@ class PPOAgent(tf_agent.TFAgent):
           'kl_cutoff_factor=0.')
     if not use_gae:
       raise NotImplementedError('Only use_gae=True is supported (PPO examples use GAE).')
-    if not compute_value_and_advantage_in_train:
-      raise NotImplementedError('compute_value_and_advantage_in_train=False is not supported.')
     if shared_vars_l2_reg:
       raise NotImplementedError('shared_vars_l2_reg needs shared actor/value variables.')
     self._optimizer = optimizer
@@ -79,6 +78,7 @@ class PPOAgent(tf_agent.TFAgent):
     self._gradient_clipping = gradient_clipping or 0.0
     self._value_clipping = value_clipping or 0.0
     self.update_normalizers_in_train = update_normalizers_in_train
+    self._compute_value_and_advantage_in_train = compute_value_and_advantage_in_train
     self._reward_normalizer = None
     if normalize_rewards:
       self._reward_normalizer = tensor_normalizer.StreamingTensorNormalizer(
@@ -89,12 +89,21 @@ class PPOAgent(tf_agent.TFAgent):
           time_step_spec.observation, scope='normalize_observations', device=device)
     policy = ppo_policy.PPOPolicy(time_step_spec, action_spec, actor_net, value_net,
                                   self._observation_normalizer, clip=False, collect=False)
-    collect_policy = ppo_policy.PPOPolicy(time_step_spec, action_spec, actor_net, value_net,
-                                          self._observation_normalizer, clip=False, collect=True,
-                                          seed=seed)
+    collect_policy = ppo_policy.PPOPolicy(
+        time_step_spec, action_spec, actor_net, value_net, self._observation_normalizer,
+        clip=False, collect=True,
+        compute_value_and_advantage_in_train=compute_value_and_advantage_in_train, seed=seed)
+    # training_data_spec = collect_data_spec + {'return', 'advantage'} when the advantages are
+    # computed by preprocess_sequence in the data pipeline (ppo_agent.py:394-409)
+    training_data_spec = None
+    if not compute_value_and_advantage_in_train:
+      info = dict(collect_policy.info_spec)
+      info['return'] = tensor_spec.TensorSpec((), torch.float32, 'return')
+      info['advantage'] = tensor_spec.TensorSpec((), torch.float32, 'advantage')
+      training_data_spec = collect_policy.trajectory_spec._replace(policy_info=info)
     super(PPOAgent, self).__init__(
         time_step_spec, action_spec, policy, collect_policy, train_sequence_length=None,
-        debug_summaries=debug_summaries, summarize_grads_and_vars=summarize_grads_and_vars,
+        training_data_spec=training_data_spec, debug_summaries=debug_summaries, summarize_grads_and_vars=summarize_grads_and_vars,
         train_step_counter=train_step_counter, device=device)
     self._nan_flag = torch.zeros(1, dtype=torch.int32, device=device)
     self._scale_dev = torch.ones(1, dtype=torch.float32, device=device)
@@ -126,8 +135,11 @@ class PPOAgent(tf_agent.TFAgent):
     if T <= 1:
       raise ValueError('Experience used for advantage calculation must have >1 num_steps.')
     dev = obs.device
-    vp, _ = self._collect_policy.apply_value_network(obs)
-    vp = vp.reshape(B, T).contiguous()
+    if self._compute_value_and_advantage_in_train:
+      vp, _ = self._collect_policy.apply_value_network(obs)
+      vp = vp.reshape(B, T).contiguous()
+    else:                                                         # :775-776
+      vp = experience.policy_info['value_prediction'].float().reshape(B, T).contiguous()
     reward = experience.reward.float().contiguous()
     if self._reward_normalizer is not None:                       # :651-654
       reward = self._reward_normalizer.normalize(reward, center_mean=False,
@@ -148,6 +160,24 @@ class PPOAgent(tf_agent.TFAgent):
       returns[:, :-1] = adv[:, :-1] + vp[:, :-1]
     return vp, returns, adv
 
+  def preprocess_sequence(self, experience):
+    """`_preprocess_sequence` (ppo_agent.py:809-832): a no-op when the advantages are computed
+    inside train(); otherwise returns `experience` with `value_prediction`, `return` and
+    `advantage` (zero for the last step) in its policy_info, for use as
+    `replay_buffer.as_dataset(sequence_preprocess_fn=agent.preprocess_sequence)`."""
+    if self._compute_value_and_advantage_in_train:
+      return experience
+    squeeze = experience.discount.dim() == 1                      # [T, ...] -> [1, T, ...]
+    if squeeze:
+      experience = nest.map_structure(lambda t: t.unsqueeze(0), experience)
+    vp, returns, adv = self._preprocess(experience)
+    info = {'dist_params': experience.policy_info['dist_params'], 'value_prediction': vp,
+            'return': returns, 'advantage': adv}
+    out = experience._replace(policy_info=info)
+    if squeeze:
+      out = nest.map_structure(lambda t: t.squeeze(0), out)
+    return out
+
   # ---- train (ppo_agent.py:834-1076) ------------------------------------------------------------
   def _train(self, experience, weights=None):
     if self._optimizer is None:
@@ -161,7 +191,12 @@ class PPOAgent(tf_agent.TFAgent):
     A = self._actor_net.num_actions
     ws, nb = workspace.get(dev)
     st = _lib.stream()
-    vp, returns, adv = self._preprocess(experience)
+    if self._compute_value_and_advantage_in_train:
+      vp, returns, adv = self._preprocess(experience)
+    else:                                                         # :843-846, :890-891, :908
+      info = experience.policy_info
+      vp, returns, adv = (info[k].float().reshape(B, T).contiguous()
+                          for k in ('value_prediction', 'return', 'advantage'))
     w = torch.empty(N, dtype=torch.float32, device=dev)
     if weights is not None:
       weights = torch.as_tensor(weights, dtype=torch.float32, device=dev).expand(B, T).contiguous()

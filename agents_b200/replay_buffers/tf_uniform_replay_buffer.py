@@ -124,6 +124,33 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
   def variables(self):
     return self._data_table.variables() + self._id_table.variables() + [self._last_id]
 
+  # ---- checkpointing (the reference checkpoints `variables()`: tf_uniform_replay_buffer.py:156-161)
+  def state_dict(self):
+    """Host copy of the ring: per-leaf storage, id table, last_id and the sampling counters."""
+    return {
+        'data': [v.detach().cpu() for v in self._data_table.variables()],
+        'ids': self._id_table.variables()[0].detach().cpu(),
+        'last_id': int(self._last_id.item()),
+        'ctrl': self._ctrl.detach().cpu(),
+        'batch_size': self._batch_size, 'max_length': self._max_length,
+    }
+
+  def load_state_dict(self, state):
+    if (state['batch_size'], state['max_length']) != (self._batch_size, self._max_length):
+      raise ValueError('Checkpointed replay buffer has batch_size={}, max_length={}; this one has '
+                       'batch_size={}, max_length={}.'.format(
+                           state['batch_size'], state['max_length'], self._batch_size,
+                           self._max_length))
+    dst = self._data_table.variables()
+    if len(dst) != len(state['data']):
+      raise ValueError('Checkpointed replay buffer has a different data_spec.')
+    for d, s in zip(dst, state['data']):
+      d.copy_(s.to(d.device))
+    self._id_table.variables()[0].copy_(state['ids'].to(self._device))
+    self._ctrl.copy_(state['ctrl'].to(self._device))
+    self._last_id.fill_(int(state['last_id']))
+    self._last_id_host = int(state['last_id'])
+
   @property
   def device(self):
     return self._device

@@ -36,6 +36,9 @@ def _agent_state_tensors(agent):
   la = getattr(agent, '_log_alpha', None)
   if isinstance(la, torch.Tensor):
     out['_log_alpha'] = la
+  upd = getattr(agent, '_update_target', None)       # Periodically counter (a tf.Variable there)
+  if isinstance(getattr(upd, '_counter', None), torch.Tensor):
+    out['_update_target/counter'] = upd._counter
   for oname in ('_optimizer', '_actor_optimizer', '_critic_optimizer', '_alpha_optimizer'):
     opt = getattr(agent, oname, None)
     if opt is not None and hasattr(opt, '_slots'):
@@ -79,6 +82,12 @@ class Learner(object):
         self.strategy.broadcast(t, src=0)
     self._last_checkpoint_step = None
     self._restore_latest()
+
+  @property
+  def train_step_numpy(self):
+    """The current train_step as a numpy scalar (learner.py:256-263)."""
+    import numpy as np
+    return np.int64(self._agent._train_step_host)
 
   # ---- checkpoints (learner.py:231-263) ----------------------------------------------------------
   def _ckpt_dir(self):

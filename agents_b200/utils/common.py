@@ -82,6 +82,101 @@ def function(fn=None, warmup=2, **unused_tf_function_kwargs):
   return _GraphFunction(fn, warmup)
 
 
+def _object_state(obj):
+  """Serializable host state of a checkpointable object."""
+  if isinstance(obj, torch.Tensor):
+    return {'tensor': obj.detach().cpu()}
+  if hasattr(obj, 'train_step_counter') and hasattr(obj, 'collect_policy'):   # a TFAgent
+    from agents_b200.train import learner as learner_lib
+    return {'agent': {k: v.detach().cpu() for k, v in
+                      learner_lib._agent_state_tensors(obj).items()},
+            'train_step': int(obj.train_step_counter.item())}
+  if hasattr(obj, 'state_dict'):
+    return {'state_dict': obj.state_dict()}
+  if hasattr(obj, 'variables'):                                               # policies, networks
+    v = obj.variables() if callable(obj.variables) else obj.variables
+    return {'variables': [t.detach().cpu() for t in v]}
+  raise TypeError('Cannot checkpoint object of type {}'.format(type(obj).__name__))
+
+
+def _restore_object(obj, state):
+  if 'tensor' in state:
+    obj.copy_(state['tensor'].to(obj.device))
+  elif 'agent' in state:
+    from agents_b200.train import learner as learner_lib
+    cur = learner_lib._agent_state_tensors(obj)
+    for k, v in state['agent'].items():
+      if k in cur:
+        cur[k].copy_(v.to(cur[k].device))
+    obj.train_step_counter.fill_(state['train_step'])
+    obj._train_step_host = state['train_step']
+  elif 'state_dict' in state:
+    obj.load_state_dict(state['state_dict'])
+  else:
+    v = obj.variables() if callable(obj.variables) else obj.variables
+    for dst, src in zip(v, state['variables']):
+      dst.copy_(src.to(dst.device))
+
+
+class Checkpointer(object):
+  """Checkpoints training state, policy state, and replay_buffer state
+  (utils/common.py:1045-1100).
+
+  `Checkpointer(ckpt_dir, max_to_keep, agent=..., replay_buffer=..., global_step=...)`: like the
+  reference, the latest checkpoint (if any) is loaded into the objects on construction
+  (:1074-1076); `save(global_step)` writes `ckpt-<step>.pt` and keeps the newest
+  `max_to_keep`.  Agents (flat parameters, optimiser slots, train_step), replay buffers (ring
+  storage, id table, last_id, Philox counters), tensors and anything with
+  `state_dict/load_state_dict` or `variables()` can be listed.
+  """
+
+  def __init__(self, ckpt_dir, max_to_keep=20, **kwargs):
+    import os
+    self._dir = ckpt_dir
+    self._max_to_keep = max_to_keep
+    self._objects = kwargs
+    os.makedirs(ckpt_dir, exist_ok=True)
+    files = self._files()
+    self._checkpoint_exists = bool(files)
+    self._restored = False
+    if files:
+      self._restore(files[-1])
+
+  def _files(self):
+    import os
+    names = [f for f in os.listdir(self._dir) if f.startswith('ckpt-') and f.endswith('.pt')]
+    return [os.path.join(self._dir, f)
+            for f in sorted(names, key=lambda f: int(f[5:-3]))]
+
+  def _restore(self, path):
+    state = torch.load(path, map_location='cpu', weights_only=False)
+    for name, obj in self._objects.items():
+      if name in state:
+        _restore_object(obj, state[name])
+    self._restored = True
+
+  @property
+  def checkpoint_exists(self):
+    return self._checkpoint_exists
+
+  def initialize_or_restore(self, session=None):
+    """Objects were restored on construction; returns whether a checkpoint was loaded."""
+    return self._restored
+
+  def save(self, global_step, options=None):
+    import os
+    step = int(global_step.item()) if isinstance(global_step, torch.Tensor) else int(global_step)
+    state = {name: _object_state(obj) for name, obj in self._objects.items()}
+    path = os.path.join(self._dir, 'ckpt-{}.pt'.format(step))
+    torch.save(state, path + '.tmp')
+    os.replace(path + '.tmp', path)
+    self._checkpoint_exists = True
+    files = self._files()
+    for f in files[:-self._max_to_keep] if self._max_to_keep else []:
+      os.remove(f)
+    return path
+
+
 def soft_variables_update(source, target, tau=1.0, tau_non_trainable=None,
                           sort_variables_by_name=False, period=1, counter=None):
   """target = (1-tau)*target + tau*source over flat buffers (utils/common.py:250-346).

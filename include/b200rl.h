@@ -346,6 +346,17 @@ int b200rl_add_scaled(float* dst, const float* src, int64_t n, float alpha, void
 int b200rl_l2_sum(const float* x, int64_t n, float coef, float* out_accum, void* stream);
 int b200rl_counter_add(int64_t* counter_dev, int64_t inc, void* stream);
 
+/* Emission order of a tf.data-style `shuffle(buffer)` over a stream of n elements, as used by
+ * PPOLearner's minibatch pipeline `cache().repeat(epochs).unbatch().shuffle(buffer).batch(mb)`
+ * (train/ppo_learner.py:220-250).  A reservoir holds the first min(buffer, n) stream elements;
+ * output i emits slot j = Philox4x32-10(counter=(i, call), key=seed) -> lo + u64 % fill and
+ * refills that slot with the next stream element (or with the last slot once the stream is
+ * exhausted).  HOST function (the reference's input pipeline is host-side too): out_host[n]
+ * receives stream indices; the rows themselves are gathered on the device
+ * (b200rl_rb_read_rows).  The reference leaves the order unpinned (tf.data RNG). */
+int b200rl_shuffle_order(int64_t n, int64_t buffer, uint64_t seed, uint64_t call,
+                         int64_t* out_host);
+
 /* ------------------------------------------------------------------------------------
  * Collect — environments + policies
  * ------------------------------------------------------------------------------------ */

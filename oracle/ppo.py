@@ -246,10 +246,33 @@ class PPOOracle(object):
     grads = self.actor.backward(atape, dm_raw) + [dstd] + self.value.backward(vtape, dv[:, None])
     return dict(loss=total, pg=pg, ve=ve, ent=en, clip_fraction=clip_frac), grads
 
-  def train(self, exp, weights=None):
-    """_train (:834-1076): preprocess once, then num_epochs full-batch steps."""
+  def preprocess_sequence(self, exp):
+    """_preprocess_sequence (:809-832) for compute_value_and_advantage_in_train=False: value
+    predictions come from policy_info (:775-776); returns / advantages are stored next to them
+    (:789-800).  Returns a copy of `exp` with 'return' and 'advantage' added."""
     B, T = exp['reward'].shape
-    vp, ret, adv = self.preprocess(exp)
+    vp = np.asarray(exp['value_prediction'], f32)
+    reward = exp['reward'][:, :-1]
+    if self.reward_normalizer is not None:
+      reward = self.reward_normalizer.normalize(reward, center_mean=False,
+                                                clip_value=self.reward_norm_clipping)
+    ret, adv = compute_return_and_advantage(reward, exp['discount'][:, :-1],
+                                            exp['next_step_type'][:, :-1], vp, self.gamma,
+                                            self.lam, self.use_gae, self.use_td)
+    pad = np.zeros((B, 1), f32)
+    out = dict(exp)
+    out['return'] = np.concatenate([ret, pad], 1)
+    out['advantage'] = np.concatenate([adv, pad], 1)
+    return out
+
+  def train(self, exp, weights=None, preprocessed=False, update_normalizers=True):
+    """_train (:834-1076): preprocess once (or take the stored return/advantage/value_prediction
+    when compute_value_and_advantage_in_train=False, :843-846), then num_epochs steps."""
+    B, T = exp['reward'].shape
+    if preprocessed:
+      vp, ret, adv = (np.asarray(exp[k], f32) for k in ('value_prediction', 'return', 'advantage'))
+    else:
+      vp, ret, adv = self.preprocess(exp)
     mask = make_trajectory_mask(exp['step_type'], ret, adv)                     # :845
     w = mask if weights is None else (np.asarray(weights, f32) * mask).astype(f32)
     A = exp['action'].shape[-1]
@@ -267,6 +290,6 @@ class PPOOracle(object):
       self.opt.apply(self.params(), grads)
       self.train_step_counter += 1
       infos.append(info)
-    if self.reward_normalizer is not None:                                      # :991-993
+    if self.reward_normalizer is not None and update_normalizers:               # :991-993
       self.reward_normalizer.update(exp['reward'])
     return infos

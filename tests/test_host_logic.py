@@ -103,3 +103,31 @@ def test_replay_buffer_requires_cuda_device():
   with pytest.raises(ValueError, match='no CPU fallback'):
     rb_mod.TFUniformReplayBuffer(tensor_spec.TensorSpec([], torch.int64), batch_size=1,
                                  device='cpu')
+
+
+def test_checkpointer_roundtrip_and_retention(tmp_path):
+  """utils/common.py:1045-1100: latest checkpoint restored on construction, max_to_keep honoured."""
+  import torch
+  from agents_b200.utils import common
+
+  class Box(object):
+    def __init__(self, v):
+      self.v = v
+    def state_dict(self):
+      return {'v': self.v}
+    def load_state_dict(self, s):
+      self.v = s['v']
+
+  step, box = torch.tensor(0, dtype=torch.int64), Box(1)
+  ck = common.Checkpointer(str(tmp_path), max_to_keep=2, global_step=step, box=box)
+  assert not ck.checkpoint_exists and ck.initialize_or_restore() is False
+  for s in (5, 10, 15):
+    step.fill_(s)
+    box.v = s * 2
+    ck.save(step)
+  import os
+  assert sorted(os.listdir(str(tmp_path))) == ['ckpt-10.pt', 'ckpt-15.pt']
+  step2, box2 = torch.tensor(0, dtype=torch.int64), Box(-1)
+  ck2 = common.Checkpointer(str(tmp_path), max_to_keep=2, global_step=step2, box=box2)
+  assert ck2.checkpoint_exists and ck2.initialize_or_restore() is True
+  assert int(step2) == 15 and box2.v == 30

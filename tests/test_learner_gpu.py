@@ -57,6 +57,33 @@ def test_learner_run_and_checkpoint(cuda):
   assert int(opt1['step'][0].item()) == 5
 
 
+def test_checkpointer_resumes_ring_agent_and_optimizer(cuda, tmp_path):
+  """common.Checkpointer (utils/common.py:1045-1100) over agent + replay buffer + global step: a
+  restored run samples the same rows and produces bit-identical losses as the original."""
+  from agents_b200.utils import common
+  agent, rb, train_step = _setup(cuda)
+  for _ in range(3):
+    exp, _ = rb.get_next(sample_batch_size=16, num_steps=2)
+    agent.train(exp)
+  ck = common.Checkpointer(str(tmp_path), max_to_keep=1, agent=agent, replay_buffer=rb,
+                           global_step=train_step)
+  assert not ck.checkpoint_exists
+  ck.save(train_step)
+  want = []
+  for _ in range(3):
+    exp, info = rb.get_next(sample_batch_size=16, num_steps=2)
+    want.append((info.ids.cpu().numpy().copy(), float(agent.train(exp).loss.item())))
+  agent2, rb2, train_step2 = _setup(cuda, seed=1)                  # different weights and data
+  ck2 = common.Checkpointer(str(tmp_path), max_to_keep=1, agent=agent2, replay_buffer=rb2,
+                            global_step=train_step2)
+  assert ck2.checkpoint_exists and ck2.initialize_or_restore()
+  assert int(train_step2.item()) == 3 and rb2.num_frames() == rb.num_frames()
+  for ids, loss in want:
+    exp, info = rb2.get_next(sample_batch_size=16, num_steps=2)
+    np.testing.assert_array_equal(info.ids.cpu().numpy(), ids)
+    assert float(agent2.train(exp).loss.item()) == loss
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs 2 GPUs (run with gpurun --gpus 2)')
 def test_nccl_data_parallel_parity():
   cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
