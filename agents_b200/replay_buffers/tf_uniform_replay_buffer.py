@@ -131,7 +131,7 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
         'data': [v.detach().cpu() for v in self._data_table.variables()],
         'ids': self._id_table.variables()[0].detach().cpu(),
         'last_id': int(self._last_id.item()),
-        'ctrl': self._ctrl.detach().cpu(),
+        'ctrl': self._ctrl.detach().cpu(), 'seed': self._seed,
         'batch_size': self._batch_size, 'max_length': self._max_length,
     }
 
@@ -148,6 +148,7 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
       d.copy_(s.to(d.device))
     self._id_table.variables()[0].copy_(state['ids'].to(self._device))
     self._ctrl.copy_(state['ctrl'].to(self._device))
+    self._seed = state.get('seed', self._seed)   # resume the same Philox stream
     self._last_id.fill_(int(state['last_id']))
     self._last_id_host = int(state['last_id'])
 
