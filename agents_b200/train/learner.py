@@ -39,6 +39,20 @@ def _agent_state_tensors(agent):
   upd = getattr(agent, '_update_target', None)       # Periodically counter (a tf.Variable there)
   if isinstance(getattr(upd, '_counter', None), torch.Tensor):
     out['_update_target/counter'] = upd._counter
+  # optimiser slots are created lazily on the first apply; materialise them for the parameter
+  # buffers each agent steps, so that a freshly built agent can be restored into
+  pairs = (('_optimizer', '_flat_params'), ('_critic_optimizer', '_critic_params'),
+           ('_alpha_optimizer', '_log_alpha'))
+  nets = (('_optimizer', '_q_network'), ('_actor_optimizer', '_actor_network'))
+  for oname, pname in pairs:
+    opt, p = getattr(agent, oname, None), getattr(agent, pname, None)
+    if hasattr(opt, '_get_slots') and isinstance(p, torch.Tensor):
+      opt._get_slots(p)
+  for oname, nname in nets:
+    opt, net = getattr(agent, oname, None), getattr(agent, nname, None)
+    if hasattr(opt, '_get_slots') and net is not None and hasattr(net, 'flat_params') and \
+        not isinstance(getattr(agent, '_flat_params', None), torch.Tensor):
+      opt._get_slots(net.flat_params)
   for oname in ('_optimizer', '_actor_optimizer', '_critic_optimizer', '_alpha_optimizer'):
     opt = getattr(agent, oname, None)
     if opt is not None and hasattr(opt, '_slots'):

@@ -175,3 +175,49 @@ def test_cartpole_collect_and_train_loop(cuda):
   frames = rb.gather_all()
   assert frames.observation.shape[1] == int(rb.num_frames())
   assert float(frames.observation.abs().max()) < 5.0
+
+
+def test_host_env_bridge_replays_driver_golden(cuda):
+  """drivers/dynamic_step_driver_test.py:121-199 through the real bridge: numpy PyEnvironmentMock
+  -> TFPyEnvironment (pinned staging, async upload) -> DynamicStepDriver -> ring."""
+  from agents_b200.environments import tf_py_environment
+  from py_env_mocks import PyEnvironmentMock
+  for num_steps, runs, isolation in [(1, 6, False), (6, 1, True)]:
+    py_env = PyEnvironmentMock()
+    env = tf_py_environment.TFPyEnvironment(py_env, check_dims=True, isolation=isolation, device=cuda)
+    assert env.batch_size == 1 and env.pyenv.envs[0] is py_env
+    policy = PolicyMock(env.time_step_spec(), env.action_spec(), cuda)
+    rb = rb_mod.TFUniformReplayBuffer(policy.trajectory_spec, batch_size=1, max_length=1000, device=cuda)
+    driver = dynamic_step_driver.DynamicStepDriver(env, policy, num_steps=num_steps,
+                                                   observers=[rb.add_batch])
+    time_step, policy_state = None, None
+    for _ in range(runs):
+      time_step, policy_state = driver.run(time_step, policy_state)
+    tr = rb.gather_all()
+    assert tr.step_type.cpu().tolist() == [[0, 1, 2, 0, 1, 2, 0, 1]]
+    assert tr.observation.cpu().tolist() == [[0, 1, 3, 0, 1, 3, 0, 1]]
+    assert tr.action.cpu().tolist() == [[1, 2, 1, 1, 2, 1, 1, 2]]
+    assert tr.next_step_type.cpu().tolist() == [[1, 2, 0, 1, 2, 0, 1, 2]]
+    assert tr.reward.cpu().tolist() == [[1., 1., 0., 1., 1., 0., 1., 1.]]
+    assert tr.discount.cpu().tolist() == [[1., 0., 1., 1., 0., 1., 1., 0.]]
+    assert py_env.actions_taken == [1, 2, 1, 2, 1, 2]        # the step after LAST ignores its action
+    env.close()
+
+
+def test_host_env_bridge_batched_and_check_dims(cuda):
+  from agents_b200.environments import batched_py_environment
+  from agents_b200.environments import tf_py_environment
+  from py_env_mocks import PyEnvironmentMock
+  py_env = batched_py_environment.BatchedPyEnvironment([PyEnvironmentMock(3), PyEnvironmentMock(4)])
+  env = tf_py_environment.TFPyEnvironment(py_env, check_dims=True, device=cuda)
+  t0 = env.reset()
+  assert t0.step_type.device.type == 'cuda' and t0.step_type.tolist() == [0, 0]
+  seen = [t0.observation.clone()]
+  for a in (1, 2, 1, 1, 2):
+    t = env.step(torch.full((2,), a, dtype=torch.int32, device=cuda))
+    seen.append(t.observation.clone())                  # staging sets alternate: clone what we keep
+  assert torch.stack(seen).cpu().tolist() == [[0, 0], [1, 1], [3, 3], [0, 4], [1, 0], [3, 2]]
+  assert env.current_time_step().step_type.tolist() == [2, 1]
+  with pytest.raises(ValueError, match='major dimension is batch_size'):
+    env.step(torch.ones(3, dtype=torch.int32, device=cuda))
+  env.close()

@@ -131,3 +131,30 @@ def test_checkpointer_roundtrip_and_retention(tmp_path):
   ck2 = common.Checkpointer(str(tmp_path), max_to_keep=2, global_step=step2, box=box2)
   assert ck2.checkpoint_exists and ck2.initialize_or_restore() is True
   assert int(step2) == 15 and box2.v == 30
+
+
+def test_batched_py_environment_contract():
+  """environments/batched_py_environment.py:60-200 + py_environment.py:185-239."""
+  import numpy as np
+  from agents_b200.environments import batched_py_environment
+  from py_env_mocks import PyEnvironmentMock
+  envs = [PyEnvironmentMock(3), PyEnvironmentMock(4)]
+  for threaded in (False, True):
+    env = batched_py_environment.BatchedPyEnvironment([PyEnvironmentMock(3), PyEnvironmentMock(4)],
+                                                      multithreading=threaded)
+    assert env.batched and env.batch_size == 2
+    t = env.step(np.array([1, 1], np.int32))            # no current step -> reset (:233-236)
+    assert t.step_type.tolist() == [0, 0] and t.observation.tolist() == [0, 0]
+    obs, types = [], []
+    for a in (1, 2, 1, 1, 2):
+      t = env.step(np.array([a, a], np.int32))
+      obs.append(t.observation.tolist()); types.append(t.step_type.tolist())
+    assert obs == [[1, 1], [3, 3], [0, 4], [1, 0], [3, 2]]
+    assert types == [[1, 1], [2, 1], [0, 2], [1, 0], [2, 1]]
+    assert t.reward.dtype == np.float32 and t.discount.tolist() == [0.0, 1.0]
+    env.close()
+  with pytest.raises(ValueError, match='already batched'):
+    batched_py_environment.BatchedPyEnvironment(
+        [batched_py_environment.BatchedPyEnvironment(envs, multithreading=False)])
+  with pytest.raises(ValueError, match='must be a list or tuple'):
+    batched_py_environment.BatchedPyEnvironment(envs[0])
