@@ -42,6 +42,8 @@ FC = (512,)
 # Mnih'15 net forward = 9.35 M MAC/sample; step = fwd(s0) + fwd_target(sn) + bwd(2x)
 FLOPS_PER_STEP = 4 * 2 * 9.35e6 * B
 GATHER_BYTES = 2 * B * T * ROW_BYTES + 8 * B * T
+WORKLOAD = (f'DQN synthetic Atari-shape obs 84x84x4 uint8, 1M-slot replay ({B_ENV}x{L}), '
+            f'batch {B}, T={T}, Mnih15 net, Huber, centered RMSProp')
 
 
 def _peaks():
@@ -186,8 +188,8 @@ def run_reference(args):
       unit='steps/s', n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2),
       ms_per_step=1000.0 / sps, higher_is_better=True, scaling='weak', vs_baseline=None,
       dtype='f32', data='synthetic',
-      config=dict(workload='DQN synthetic Atari-shape obs 84x84x4 uint8, batch 256, T=2, '
-                           'Mnih15 net, Huber, RMSProp', global_batch=B, parallelism='cpu'),
+      config=dict(workload=WORKLOAD, global_batch=B, per_gpu_batch=B, num_actions=A,
+                  parallelism='cpu (host cores of the box, rank 0 only)'),
       cpu_baseline=dict(value=sps, unit='steps/s', cores=cores, kind='port', sample=sample),
       e2e=dict(value=sps, unit='steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   print(json.dumps(line), flush=True)
@@ -434,9 +436,7 @@ def main():
         metric='train steps/sec (DQN Atari-shape, batch 256)', value=value, unit='steps/s',
         n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
         scaling='weak', vs_baseline=None, dtype='f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)', data='synthetic',
-        config=dict(workload='DQN synthetic Atari-shape obs 84x84x4 uint8, 1M-slot replay '
-                             f'({B_ENV}x{L}), batch {B}, T={T}, Mnih15 net, Huber, centered RMSProp',
-                    global_batch=B * world, per_gpu_batch=B, num_actions=A,
+        config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, num_actions=A,
                     parallelism=f'dp{world}' if world > 1 else 'single',
                     l2='inputs > L2: 29.6 GB ring, fresh random rows every step',
                     cuda_graph=bool(use_graph), collect_frames_per_e2e_step=B_ENV,
