@@ -731,7 +731,7 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
                       const float* dY, float* dX, float* dW, float* db,
                       const b200rl_conv_t* c, int accumulate, void* workspace,
                       int64_t ws_bytes, void* stream) {
-  B200RL_CHECK_ARG(X && Wt && dY && dW, "conv2d_bwd: NULL argument");
+  B200RL_CHECK_ARG(X && Wt && dY, "conv2d_bwd: NULL argument");
   B200RL_CHECK_ARG(!(dX && x_is_u8), "conv2d_bwd: no input gradient for u8 input");
   ConvGeom cg;
   int rc = make_geom(c, cg);
@@ -739,7 +739,7 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
   const int64_t F = c->F;
-  {  // dW[K,F] = im2col(X)^T @ dY
+  if (dW) {  // dW[K,F] = im2col(X)^T @ dY
     GemmArgs g{dW, nullptr, K, F, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
     if (x_is_u8 && gemm_mode() == 1 && F >= 16 && K >= 32 && M >= 8) {
       g.out_scale = 1.f / x_scale;

@@ -158,16 +158,21 @@ class Dense(Layer):
               self.units, self._act, _lib.ptr(ws), nb, _lib.stream())
     return y
 
-  def backward(self, x, y, dy, need_dx, need_dw=True):
+  def backward_act(self, y, dy):
+    """dLoss/d(pre-activation) from dLoss/d(output)."""
+    dy = dy.contiguous()
+    if self._act == _lib.ACT_NONE:
+      return dy
+    dz = torch.empty_like(dy)
+    _lib.call('b200rl_act_bwd', _lib.ptr(y), _lib.ptr(dy), _lib.ptr(dz), dy.numel(), self._act,
+              _lib.stream())
+    return dz
+
+  def backward_parts(self, x, dz, need_dx, need_dw):
+    """Input gradient and/or parameter gradients from dz (either half may be skipped, so that the
+    two halves can run on different streams)."""
     x, ldx = _batch_strided(x, self.in_features)
     m = x.shape[0]
-    dy = dy.contiguous()
-    if self._act != _lib.ACT_NONE:
-      dz = torch.empty_like(dy)
-      _lib.call('b200rl_act_bwd', _lib.ptr(y), _lib.ptr(dy), _lib.ptr(dz), dy.numel(), self._act,
-                _lib.stream())
-    else:
-      dz = dy
     dx = torch.empty((m, self.in_features), dtype=torch.float32, device=x.device) if need_dx else None
     ws, nb = workspace.get(x.device)
     _lib.call('b200rl_dense_bwd', _lib.dptr(x), ldx, _lib.ptr(self.kernel), _lib.ptr(dz),
@@ -175,6 +180,9 @@ class Dense(Layer):
               _lib.ptr(self.d_bias) if need_dw else None, m, self.in_features,
               self.units, 0, _lib.ptr(ws), nb, _lib.stream())
     return dx
+
+  def backward(self, x, y, dy, need_dx, need_dw=True):
+    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw)
 
 
 class Conv2D(Layer):
@@ -249,17 +257,19 @@ class Conv2D(Layer):
               _lib.ptr(ws), nb, _lib.stream())
     return y
 
-  def backward(self, x, y, dy, need_dx):
+  def backward_act(self, y, dy):
+    dy = dy.contiguous()
+    if self._act == _lib.ACT_NONE:
+      return dy
+    dz = torch.empty_like(dy)
+    _lib.call('b200rl_act_bwd', _lib.ptr(y), _lib.ptr(dy), _lib.ptr(dz), dy.numel(), self._act,
+              _lib.stream())
+    return dz
+
+  def backward_parts(self, x, dz, need_dx, need_dw):
     x, bstride, is_u8 = self._input(x)
     g = self._geom(x)
     g.x_batch_stride = bstride
-    dy = dy.contiguous()
-    if self._act != _lib.ACT_NONE:
-      dz = torch.empty_like(dy)
-      _lib.call('b200rl_act_bwd', _lib.ptr(y), _lib.ptr(dy), _lib.ptr(dz), dy.numel(), self._act,
-                _lib.stream())
-    else:
-      dz = dy
     dx = None
     need = 0
     if need_dx:
@@ -267,6 +277,11 @@ class Conv2D(Layer):
       need = x.shape[0] * self.oh * self.ow * self.kh * self.kw * self.c * 4
     ws, nb = workspace.get(x.device, need)
     _lib.call('b200rl_conv2d_bwd', _lib.dptr(x), int(is_u8), float(self.pre_divisor or 1.0),
-              _lib.ptr(self.kernel), _lib.ptr(dz), _lib.ptr(dx), _lib.ptr(self.d_kernel),
-              _lib.ptr(self.d_bias), ctypes.byref(g), 0, _lib.ptr(ws), nb, _lib.stream())
+              _lib.ptr(self.kernel), _lib.ptr(dz), _lib.ptr(dx),
+              _lib.ptr(self.d_kernel) if need_dw else None,
+              _lib.ptr(self.d_bias) if need_dw else None, ctypes.byref(g), 0, _lib.ptr(ws), nb,
+              _lib.stream())
     return dx
+
+  def backward(self, x, y, dy, need_dx, need_dw=True):
+    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw)

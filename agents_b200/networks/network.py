@@ -6,12 +6,14 @@ returns `(output, network_state)` like the reference; `forward_train` additional
 the activations needed by `backward`.
 """
 import copy as _copy
+import os
 
 import numpy as np
 import torch
 
 from agents_b200.networks import layers as layers_lib
 from agents_b200.utils import nest
+from agents_b200.utils import workspace
 
 
 class Network(object):
@@ -206,16 +208,45 @@ class Network(object):
     w.r.t. their action input); need_param_grads=False skips the weight gradients (dense only).
     Returns flat_grads, or (flat_grads, d_input) when need_input_grad."""
     first = next(i for i, (l, _, _) in enumerate(tape) if l.has_params)
+    # Inside a captured graph the parameter gradients (dW GEMM + bias column sum) of every
+    # layer are forked onto a side stream: only the dX chain stays on the critical path.
+    side = _side_stream(self._device) if (
+        _BWD_OVERLAP and need_param_grads and torch.cuda.is_current_stream_capturing()) else None
+    main = torch.cuda.current_stream() if side is not None else None
     for i in range(len(tape) - 1, -1, -1):
       l, x, y = tape[i]
       need_dx = need_input_grad or i > first
-      if not need_param_grads and isinstance(l, layers_lib.Dense):
+      if side is not None and hasattr(l, 'backward_parts'):
+        dz = l.backward_act(y, dy)
+        side.wait_stream(main)                   # dz (and everything before it) is ready
+        dz.record_stream(side)
+        with torch.cuda.stream(side), workspace.slot(1):
+          l.backward_parts(x, dz, need_dx=False, need_dw=True)
+        dy = l.backward_parts(x, dz, need_dx=True, need_dw=False) if need_dx else None
+      elif not need_param_grads and isinstance(l, layers_lib.Dense):
         dy = l.backward(x, y, dy, need_dx=need_dx, need_dw=False)
       else:
         dy = l.backward(x, y, dy, need_dx=need_dx)
+    if side is not None:
+      main.wait_stream(side)
+    elif _BWD_OVERLAP and not torch.cuda.is_current_stream_capturing():
+      workspace.mirror(self._device, 1)          # size the side-stream scratch for a later capture
+      _side_stream(self._device)
     if need_input_grad:
       return self._grads, dy
     return self._grads
+
+
+_BWD_OVERLAP = os.environ.get('B200RL_BWD_OVERLAP', '1') != '0'
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+  device = torch.device(device)
+  key = device.index if device.index is not None else torch.cuda.current_device()
+  if key not in _SIDE_STREAMS:
+    _SIDE_STREAMS[key] = torch.cuda.Stream(device=device)
+  return _SIDE_STREAMS[key]
 
 
 def allocate_jointly(networks):

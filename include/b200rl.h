@@ -307,6 +307,8 @@ typedef struct {
 int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
                       const float* bias, float* Y, const b200rl_conv_t* g, int act,
                       void* workspace, int64_t ws_bytes, void* stream);
+/* dX, dW and db may each be NULL (that gradient is skipped), so the parameter gradients and the
+ * input gradient of one layer can be issued on different streams. */
 int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
                       const float* dY, float* dX, float* dW, float* db,
                       const b200rl_conv_t* g, int accumulate, void* workspace,
