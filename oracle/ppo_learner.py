@@ -8,8 +8,11 @@ Follows tf_agents/train/ppo_learner.py:
     `int(num_frames / mb) * num_epochs / num_replicas` train iterations (or
     `num_samples * num_epochs / num_replicas` without minibatching);
   * `_update_normalizers` (:306-337).
-The shuffle order is unpinned in the reference (tf.data RNG); ours is defined in
-include/b200rl.h (b200rl_shuffle_order) and restated here in pure Python.
+Pinned against the reference's own expectations (train/ppo_learner_test.py:193-376: train-call
+counts 10/20/60/1/2/2, 12/24/72/3/6/6, 48 and the exact minibatch contents with
+shuffle_buffer_size=1) in tests/test_ppo_learner_host.py.  The shuffle order for buffer > 1 is
+unpinned in the reference (tf.data RNG); ours is defined in include/b200rl.h
+(b200rl_shuffle_order) and restated here in pure Python.
 """
 import numpy as np
 

@@ -54,3 +54,41 @@ def test_constructor_checks():
                            shuffle_buffer_size=16)
   with pytest.raises(ValueError, match='update_normalizers_in_train should be set to False'):
     ppo_learner.PPOLearner('/tmp/x', None, _fake_agent(False, True), ds, ds, 1)
+
+
+# ---- train/ppo_learner_test.py replayed on the oracle restatement -----------------------------------
+def _reference_observations(n_time_steps, batch_size):
+  """ppo_learner_test.py:83-96 `_create_trajectories`: obs[b, t] = 10 b + t."""
+  return np.asarray([np.arange(n_time_steps) + 10 * i for i in range(batch_size)], np.float32)
+
+
+@pytest.mark.parametrize('num_epochs,envs,mb,expected', [
+    (1, 1, 10, 10), (2, 1, 10, 20), (2, 3, 10, 60), (1, 1, None, 1), (2, 1, None, 2), (2, 3, None, 2)])
+def test_reference_one_element_dataset(num_epochs, envs, mb, expected):   # :193-253
+  obs = _reference_observations(100, envs)
+  n = obs.size
+  assert opl.iterations_per_run(n, 1, num_epochs, mb, 1) == expected
+  if mb:
+    rows = opl.minibatch_rows(n, num_epochs, mb, shuffle_buffer_size=1, seed=0, call=0)
+    stream = np.concatenate([obs] * num_epochs, 0).reshape(-1)      # _concat_and_flatten (:133-152)
+    for i in range(expected):                                      # _get_expected_minibatch (:155-178)
+      np.testing.assert_array_equal(obs.reshape(-1)[rows[i]], stream[mb * i:mb * (i + 1)])
+
+
+@pytest.mark.parametrize('num_epochs,envs,mb,expected', [
+    (1, 1, 10, 12), (2, 1, 10, 24), (2, 3, 10, 72), (1, 1, None, 3), (2, 1, None, 6), (2, 3, None, 6)])
+def test_reference_multi_element_dataset(num_epochs, envs, mb, expected):  # :255-329
+  episodes = 3
+  obs = _reference_observations(40, envs)
+  cache = np.concatenate([obs.reshape(-1)] * episodes)             # 3 cached samples, unbatched
+  n = cache.size
+  assert opl.iterations_per_run(n, episodes, num_epochs, mb, 1) == expected
+  if mb:
+    rows = opl.minibatch_rows(n, num_epochs, mb, shuffle_buffer_size=1, seed=0, call=0)
+    stream = np.concatenate([obs] * (episodes * num_epochs), 0).reshape(-1)
+    for i in range(expected):
+      np.testing.assert_array_equal(cache[rows[i]], stream[mb * i:mb * (i + 1)])
+
+
+def test_reference_parallel_iterations_count():                           # :331-376
+  assert opl.iterations_per_run(3 * 40, 3, 4, 10, 1) == 48
