@@ -149,65 +149,3 @@ def test_full_sequence_mode(cuda, tmp_path):
   lrn.run()
   assert int(agent.train_step_counter.item()) == 6
   assert lrn.train_step_numpy == 6
-
-
-# ---- train/ppo_learner_test.py replayed through the real pipeline ---------------------------------
-class _FakePPOAgent(object):
-  """ppo_learner_test.py:41-79 FakePPOAgent: counts train() calls and keeps what it was fed."""
-
-  def __init__(self, device):
-    from agents_b200.agents import tf_agent
-    self._loss_info = tf_agent.LossInfo(torch.zeros((), device=device), ())
-    self._compute_value_and_advantage_in_train = False
-    self.update_normalizers_in_train = False
-    self.train_step_counter = torch.zeros((), dtype=torch.int64, device=device)
-    self._train_step_host = 0
-    self.experiences = []
-
-  def train(self, experience, weights=None):
-    self.experiences.append(experience)
-    self._train_step_host += 1
-    return self._loss_info
-
-  def update_observation_normalizer(self, batched_observations):
-    pass
-
-  def update_reward_normalizer(self, batched_rewards):
-    pass
-
-
-def _reference_trajectories(cuda, n_time_steps, batch_size):
-  """ppo_learner_test.py:82-130 `_create_trajectories`: obs[b, t, 0] = 10 b + t, the rest ones."""
-  obs = torch.as_tensor(np.asarray([np.arange(n_time_steps) + 10 * i for i in range(batch_size)], f32)[..., None],
-                        device=cuda)
-  ones = torch.ones(batch_size, n_time_steps, device=cuda)
-  mid = torch.ones(batch_size, n_time_steps, dtype=torch.int32, device=cuda)
-  info = {'dist_params': {'loc': ones[..., None].clone(), 'scale': ones[..., None].clone()},
-          'value_prediction': ones.clone(), 'return': ones.clone(), 'advantage': ones.clone()}
-  return trajectory.Trajectory(mid, obs, ones[..., None].clone(), info, mid.clone(), ones.clone(), ones.clone())
-
-
-@pytest.mark.parametrize('episodes,steps,num_epochs,envs,mb,expected', [
-    (1, 100, 1, 1, 10, 10), (1, 100, 2, 1, 10, 20), (1, 100, 2, 3, 10, 60),       # :193-253
-    (1, 100, 1, 1, None, 1), (1, 100, 2, 3, None, 2),
-    (3, 40, 1, 1, 10, 12), (3, 40, 2, 3, 10, 72), (3, 40, 2, 1, None, 6),          # :255-329
-    (3, 40, 4, 1, 10, 48)])                                                          # :331-376
-def test_reference_ppo_learner_cases(cuda, tmp_path, episodes, steps, num_epochs, envs, mb, expected):
-  traj = _reference_trajectories(cuda, steps, envs)
-  dataset_fn = lambda: [(traj, ())] * episodes
-  agent = _FakePPOAgent(cuda)
-  lrn = ppo_learner.PPOLearner(str(tmp_path), agent.train_step_counter, agent, dataset_fn, dataset_fn,
-                               num_samples=episodes, num_epochs=num_epochs, minibatch_size=mb,
-                               shuffle_buffer_size=1, checkpoint_interval=0)    # buffer 1 = no shuffling
-  loss = lrn.run()
-  assert len(agent.experiences) == expected and float(loss.loss.item()) == 0.0
-  want_obs = traj.observation.reshape(-1).cpu().numpy()
-  if mb:
-    stream = np.concatenate([want_obs] * (episodes * num_epochs))   # _concat_and_flatten (:133-152)
-    for i, got in enumerate(agent.experiences):                     # _get_expected_minibatch (:155-178)
-      assert tuple(got.observation.shape) == (mb, 1, 1) and tuple(got.reward.shape) == (mb, 1)
-      np.testing.assert_array_equal(got.observation.reshape(-1).cpu().numpy(), stream[mb * i:mb * (i + 1)])
-      assert set(got.policy_info) == {'dist_params', 'value_prediction', 'return', 'advantage'}
-  else:
-    for got in agent.experiences:
-      assert got is traj
