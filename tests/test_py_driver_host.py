@@ -91,3 +91,28 @@ def test_batched_environment(max_steps, max_episodes, expected):    # :235-327
   drv.run(env.reset(), policy.get_initial_state())
   assert [_as_dict(t) for t in seen] == want[:expected]
   env.close()
+
+
+def test_parallel_py_environment_matches_batched():
+  """environments/parallel_py_environment.py: worker processes give the same batched stream as
+  the in-process BatchedPyEnvironment; worker exceptions surface in the parent."""
+  from agents_b200.environments import parallel_py_environment
+  ctors = [lambda: PyEnvironmentMock(3), lambda: PyEnvironmentMock(4), lambda: PyEnvironmentMock(5)]
+  for blocking in (False, True):
+    par = parallel_py_environment.ParallelPyEnvironment(ctors, start_serially=not blocking, blocking=blocking)
+    ref = batched_py_environment.BatchedPyEnvironment([c() for c in ctors], multithreading=False)
+    assert par.batched and par.batch_size == 3 and par.action_spec() == ref.action_spec()
+    a, b = par.reset(), ref.reset()
+    for step in range(12):
+      for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)
+      act = np.array([1 + (step + i) % 2 for i in range(3)], np.int32)
+      a, b = par.step(act), ref.step(act)
+    par.close(); ref.close()
+  with pytest.raises(TypeError, match='non-callable'):
+    parallel_py_environment.ParallelPyEnvironment([PyEnvironmentMock()])
+
+  def broken():
+    raise ValueError('boom in worker')
+  with pytest.raises(RuntimeError, match='boom in worker'):
+    parallel_py_environment.ParallelPyEnvironment([broken])
