@@ -450,7 +450,11 @@ def main():
                       achieved=update_tfs, peak=peaks['tensor'], unit='TFLOP/s',
                       frac=update_tfs / peaks['tensor'], traffic=traffic.get('update'),
                       peak_source=peaks['src'] + ' bf16 sustained', ms=update_ms,
-                      algorithmic_flops=FLOPS_PER_STEP),
+                      algorithmic_flops=FLOPS_PER_STEP,
+                      # fp32-equivalent ceiling of the arithmetic actually used: TF32 runs at half
+                      # the bf16 rate and 3xTF32 issues three MMAs per product -> peak / 6
+                      tf32x3_equiv_peak=peaks['tensor'] / 6.0,
+                      frac_of_tf32x3_equiv=update_tfs / (peaks['tensor'] / 6.0)),
         roofline_gather=dict(kernel='row_copy_tma<MODE_SAMPLE> (cp.async.bulk)', bound='hbm', achieved=gather_gbs,
                              peak=peaks['hbm'], unit='GB/s', frac=gather_gbs / peaks['hbm'],
                              traffic=traffic.get('gather'), peak_source=peaks['src'],
