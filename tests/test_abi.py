@@ -49,3 +49,25 @@ def test_struct_layout_matches_header():
   assert ctypes.sizeof(_lib.Leaf) == 16
   assert ctypes.sizeof(_lib.Ring) == 8 + 8 + 8 + 8 + 8 + 8 + 16 * _lib.MAX_LEAVES
   assert ctypes.sizeof(_lib.ConvGeom) == 40
+
+
+def test_integration_md_stub_matches_the_binding():
+  """The ctypes stub printed in INTEGRATION.md must stay loadable and layout-compatible with the
+  binding the package uses (struct layout, symbol, argument count)."""
+  import ctypes
+  import os
+  import re
+  from agents_b200 import _lib
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  text = open(os.path.join(root, 'INTEGRATION.md')).read()
+  block = re.search(r"```python\nimport ctypes\n(.*?)```", text, re.S).group(1)
+  block = block.replace("ctypes.CDLL('libb200rl.so')", "ctypes.CDLL(%r)" % _lib.LIB_PATH)
+  ns = {'ctypes': ctypes}
+  exec('import ctypes\n' + block, ns)              # defines lib, Leaf, Ring, fused_read
+  assert ctypes.sizeof(ns['Ring']) == ctypes.sizeof(_lib.Ring)
+  assert ctypes.sizeof(ns['Leaf']) == ctypes.sizeof(_lib.Leaf)
+  for (name, _), (name2, _) in zip(ns['Ring']._fields_, _lib.Ring._fields_):
+    assert name == name2
+    assert getattr(ns['Ring'], name).offset == getattr(_lib.Ring, name2).offset
+  assert len(ns['lib'].b200rl_rb_read_rows.argtypes) == len(_lib.SIGNATURES['b200rl_rb_read_rows'])
+  assert callable(ns['fused_read'])
