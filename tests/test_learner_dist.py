@@ -110,3 +110,47 @@ def test_shard_range_errors_and_default_strategy():
   s = strategy_utils.SingleProcessStrategy()
   assert s.shard_range(7) == (0, 7) and s.num_replicas_in_sync == 1
   assert isinstance(strategy_utils.get_strategy(), strategy_utils.SingleProcessStrategy)
+
+
+def _ppo_worker(rank, world, port, out_dir):
+  """PPOLearner under 2 gloo replicas, full-sequence mode (host only): the number of train
+  calls per replica is num_samples * num_epochs / num_replicas (train/ppo_learner.py:283-300)
+  and the LossInfo returned by run() is SUM-reduced."""
+  import collections
+  from agents_b200.train import ppo_learner
+  os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+  dist.init_process_group('gloo', rank=rank, world_size=world)
+  strategy = strategy_utils.ProcessGroupStrategy()
+  agent = FakeAgent()
+  agent._compute_value_and_advantage_in_train = False
+  agent.update_normalizers_in_train = False
+  agent.update_observation_normalizer = lambda obs: None
+  agent.update_reward_normalizer = lambda r: None
+  calls = []
+  agent.train = lambda exp: (calls.append(1), agent.__class__.loss(agent, exp))[1]
+  Traj = collections.namedtuple('Traj', ['observation', 'reward', 'xy'])
+  g = torch.Generator().manual_seed(rank)
+  x, y = torch.randn(4, 3, generator=g), torch.randn(4, generator=g)
+
+  class Exp(Traj):                       # what FakeAgent.loss unpacks: (x, y)
+    def __iter__(self):
+      return iter(self.xy)
+  sample = Exp(observation=x, reward=torch.zeros(4, 6), xy=(x, y))
+  ds = lambda: [sample] * 3
+  lrn = ppo_learner.PPOLearner(out_dir, agent.train_step_counter, agent, ds, ds, num_samples=3, num_epochs=4,
+                               strategy=strategy, checkpoint_interval=0)
+  info = lrn.run()
+  local = float(agent.__class__.loss(agent, sample).loss)
+  torch.save({'calls': len(calls), 'frames': lrn.num_frames_for_training, 'loss': float(info.loss),
+              'local': local}, os.path.join(out_dir, f'p{rank}.pt'))
+  dist.destroy_process_group()
+
+
+def test_ppo_learner_iterations_under_two_replicas():
+  out = tempfile.mkdtemp()
+  mp.spawn(_ppo_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+  r0, r1 = torch.load(os.path.join(out, 'p0.pt')), torch.load(os.path.join(out, 'p1.pt'))
+  assert r0['calls'] == r1['calls'] == 3 * 4 // 2            # 12 batches over 2 replicas
+  assert r0['frames'] == r1['frames'] == 3 * 4 * 6
+  np.testing.assert_allclose(r0['loss'], r0['local'] + r1['local'], rtol=1e-5)   # SUM over replicas
+  np.testing.assert_allclose(r1['loss'], r0['loss'], rtol=1e-6)
