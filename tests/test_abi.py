@@ -71,3 +71,24 @@ def test_integration_md_stub_matches_the_binding():
     assert getattr(ns['Ring'], name).offset == getattr(_lib.Ring, name2).offset
   assert len(ns['lib'].b200rl_rb_read_rows.argtypes) == len(_lib.SIGNATURES['b200rl_rb_read_rows'])
   assert callable(ns['fused_read'])
+
+
+def test_every_entry_point_is_documented_in_integration_md():
+  """INTEGRATION.md's entry-point table must mention every symbol the header declares
+  (shorthands `a_fwd/bwd`, `a[_ld]` and `a_*` are expanded)."""
+  import os
+  import re
+  root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+  header = open(os.path.join(root, 'include', 'b200rl.h')).read()
+  doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+  symbols = sorted(set(re.findall(r'\b(b200rl_[a-z0-9_]+)\s*\(', header)))
+  covered = set()
+  for m in re.finditer(r'`(b200rl_[a-z0-9_]+)/([a-z0-9_/]+)`', doc):
+    stem = m.group(1)[:m.group(1).rfind('_') + 1]
+    covered.update([m.group(1)] + [stem + a for a in m.group(2).split('/')])
+  for m in re.finditer(r'`(b200rl_[a-z0-9_]+)\[(_[a-z0-9]+)\]`', doc):
+    covered.update([m.group(1), m.group(1) + m.group(2)])
+  prefixes = [m.group(1) + '_' for m in re.finditer(r'`(b200rl_[a-z0-9_]+)_\*`', doc)]
+  missing = [s for s in symbols
+             if s not in doc and s not in covered and not any(s.startswith(p) for p in prefixes)]
+  assert not missing, missing
