@@ -104,6 +104,7 @@ SIGNATURES = {
     'b200rl_l2_sum': [_P, c_i64, c_f32, _P, _P],
     'b200rl_counter_add': [_P, c_i64, _P],
     'b200rl_shuffle_order': [c_i64, c_i64, c_u64, c_u64, _P],
+    'b200rl_rb_gather_frame_stack': [_P, _P, c_i64, c_i64, _P, _P, c_i64, c_i64, c_int, _P, _P],
     'b200rl_epsilon_greedy': [_P, _P, c_i64, c_i64, c_f32, c_u64, _P, _P, _P, _P, _P],
     'b200rl_env_random_step': [_P, _P, _P, c_i64, c_int, _P, _P, c_i64, c_f32, c_u64, _P, _P],
     'b200rl_env_cartpole_step': [_P, _P, _P, _P, _P, _P, _P, c_i64, ctypes.c_int32, c_u64, _P,

@@ -114,6 +114,20 @@ int b200rl_rb_gather_all(const b200rl_ring_t* ring, int64_t n_valid, void* const
 /* _clear (tf_uniform_replay_buffer.py:559-579): last_id = -1; zero tables when clear_all. */
 int b200rl_rb_clear(const b200rl_ring_t* ring, int clear_all, void* stream);
 
+/* Frame-dedup gather (no TFUniformReplayBuffer counterpart; the reference de-duplicates frames
+ * only in the host-side PyHashedReplayBuffer, replay_buffers/py_hashed_replay_buffer.py:37-181).
+ * frames: [batch_size*max_length, frame_bytes] uint8 ring leaf holding ONE frame per slot;
+ * step_type: the ring's int32 step_type leaf.  For every sampled window start ids_dev[b] in segment
+ * offsets_dev[b] and every t < T, out[b, t] (frame_bytes * K bytes, pixel-major / channel-minor,
+ * i.e. [H, W, K]) receives the K most recent frames of the item's episode: channel c = frame of id
+ * max(id - (K-1-c), id of the episode's FIRST step) (semantics: oracle/frame_stack.py).
+ * frame_bytes must be a multiple of 4, 1 <= K <= 4.  The caller keeps ids whose look-back would
+ * reach overwritten slots out of ids_dev. */
+int b200rl_rb_gather_frame_stack(const void* frames, const int32_t* step_type,
+                                 int64_t frame_bytes, int64_t max_length,
+                                 const int64_t* ids_dev, const int64_t* offsets_dev, int64_t B,
+                                 int64_t T, int32_t K, void* out, void* stream);
+
 /* Philox draw alone (tf_uniform_replay_buffer.py:265-272) — same stream as b200rl_rb_sample. */
 int b200rl_rb_draw(const b200rl_ring_t* ring, int64_t B, int64_t T, uint64_t seed,
                    uint64_t* rng_call_dev, int64_t* out_ids, int64_t* out_offs, void* stream);

@@ -100,3 +100,54 @@ def test_py_driver_feeds_the_ring(cuda):
   assert tr.reward.cpu().tolist() == [[1., 1., 0., 1., 1., 0., 1., 1.]]
   assert tr.discount.cpu().tolist() == [[1., 0., 1., 1., 0., 1., 1., 0.]]
   env.close()
+
+
+@pytest.mark.xfail(strict=False, reason='frame-dedup kernel and buffer were written without GPU access; '
+                                        'first executed by the round-end run')
+@pytest.mark.parametrize('K,L,adds', [(4, 16, 11), (4, 8, 29), (3, 8, 20), (2, 8, 9)])
+def test_frame_stack_buffer_rebuilds_the_stored_stacks(cuda, K, L, adds):
+  """FrameStackReplayBuffer (one frame per slot) returns, for the ids it samples, exactly the
+  stacks a FrameStack-K producer emitted (oracle/frame_stack.py), across episode starts and after
+  the ring wrapped; the other leaves come back as in TFUniformReplayBuffer."""
+  from agents_b200.replay_buffers import frame_stack_replay_buffer as fsrb
+  from agents_b200.specs import tensor_spec
+  from oracle import frame_stack as ofs
+  rng = np.random.RandomState(K * 100 + adds)
+  B_env, H, W = 3, 6, 6
+  frames = rng.randint(0, 256, size=(B_env, adds, H, W)).astype(np.uint8)
+  step_types = rng.choice([0, 1, 1, 1, 2], size=(B_env, adds)).astype(np.int32)
+  step_types[:, 0] = 0
+  for b in range(B_env):
+    for t in range(1, adds):
+      if step_types[b, t - 1] == 2:
+        step_types[b, t] = 0
+  stacks = np.stack([ofs.stack_rule(frames[b], step_types[b], K) for b in range(B_env)])   # [B_env, adds, H, W, K]
+  spec = trajectory.Trajectory(
+      step_type=tensor_spec.TensorSpec([], torch.int32, 'step_type'),
+      observation=tensor_spec.TensorSpec((H, W, K), torch.uint8, 'observation'),
+      action=tensor_spec.TensorSpec([], torch.int32, 'action'), policy_info=(),
+      next_step_type=tensor_spec.TensorSpec([], torch.int32, 'next_step_type'),
+      reward=tensor_spec.TensorSpec([], torch.float32, 'reward'),
+      discount=tensor_spec.TensorSpec([], torch.float32, 'discount'))
+  rb = fsrb.FrameStackReplayBuffer(spec, batch_size=B_env, max_length=L, device=cuda, seed=5)
+  assert rb.stack_depth == K
+  d = lambda a: torch.as_tensor(a, device=cuda)
+  for t in range(adds):
+    obs = d(stacks[:, t]) if t % 2 == 0 else d(frames[:, t])       # stacked and single-frame producers
+    rb.add_batch(trajectory.Trajectory(
+        d(step_types[:, t]), obs, d(np.arange(B_env, dtype=np.int32)), (), d(step_types[:, t]),
+        d(np.full(B_env, t, f32)), d(np.ones(B_env, f32))))
+  oldest = max(0, adds - L)
+  for B, T in [(8, 1), (5, 2), (16, 3)]:
+    data, info = rb.get_next(sample_batch_size=B, num_steps=T)
+    ids = info.ids.cpu().numpy()
+    env = data.action.cpu().numpy()                                  # action leaf = segment index
+    got = data.observation.cpu().numpy()
+    assert got.shape == (B, T, H, W, K) and ids.shape == (B, T)
+    assert (ids[:, 0] >= oldest + K - 1).all() and (ids[:, -1] <= adds - 1).all()
+    np.testing.assert_array_equal(data.reward.cpu().numpy(), ids.astype(f32))   # reward leaf = id
+    for b in range(B):
+      for t in range(T):
+        np.testing.assert_array_equal(got[b, t], stacks[env[b, t], ids[b, t]])
+  one, info1 = rb.get_next()                                           # unbatched, single step
+  assert tuple(one.observation.shape) == (H, W, K) and info1.ids.dim() == 0
