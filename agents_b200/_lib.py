@@ -44,6 +44,11 @@ class ConvGeom(ctypes.Structure):
              ] + [('x_batch_stride', ctypes.c_int64)]
 
 
+class PpoKl(ctypes.Structure):
+  _fields_ = [('old_loc', c_void_p), ('old_scale', c_void_p), ('ld_old', c_i64),
+              ('terms', c_void_p), ('grad_scale', c_f32)]
+
+
 class B200RLError(RuntimeError):
   pass
 
@@ -52,6 +57,7 @@ class B200RLError(RuntimeError):
 _P = c_void_p
 SIGNATURES = {
     'b200rl_set_copy_variant': [c_int],
+    'b200rl_set_pdl': [c_int],
     'b200rl_rb_add_batch': [ctypes.POINTER(Ring), _P, _P],
     'b200rl_rb_sample': [ctypes.POINTER(Ring), c_i64, c_i64, _P, _P, c_u64, _P, _P, _P, _P, _P,
                          _P, _P],
@@ -65,7 +71,10 @@ SIGNATURES = {
     'b200rl_discounted_return_ld': [_P, _P, _P, _P, c_i64, c_i64, c_i64, c_i64, c_i64, _P],
     'b200rl_gae_ld': [_P, _P, _P, _P, c_f32, _P, c_i64, c_i64, c_i64, c_i64, c_i64, _P],
     'b200rl_ppo_loss': [_P, _P, c_i64, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_f32, c_f32,
-                        c_f32, c_f32, c_f32, c_f32, _P, _P, _P, c_i64, _P, _P, _P, c_i64, _P],
+                        c_f32, c_f32, c_f32, c_f32, _P, _P, _P, c_i64, _P, _P, _P, _P, c_i64, _P],
+    'b200rl_ppo_kl': [_P, _P, c_i64, _P, _P, c_i64, _P, c_i64, c_i64, c_f32, _P, _P, _P, c_i64, _P],
+    'b200rl_ppo_kl_terms': [_P, _P, c_f32, c_f32, c_f32, _P, _P],
+    'b200rl_ppo_kl_beta_update': [_P, _P, c_f32, c_f32, _P],
     'b200rl_normal_logp': [_P, _P, c_i64, _P, c_i64, c_i64, _P, _P],
     'b200rl_normal_sample': [_P, _P, c_i64, c_i64, c_i64, _P, _P, c_u64, _P, _P, _P],
     'b200rl_normal_proj_fwd': [_P, _P, _P, _P, c_i64, c_i64, _P, _P, _P],
@@ -89,12 +98,13 @@ SIGNATURES = {
     'b200rl_tc_debug_buffer': [_P],
     'b200rl_tc_debug_variant': [c_int],
     'b200rl_dense_fwd': [_P, c_i64, _P, _P, _P, c_i64, c_i64, c_i64, c_int, _P, c_i64, _P],
-    'b200rl_dense_bwd': [_P, c_i64, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_int, _P, c_i64, _P],
+    'b200rl_dense_bwd': [_P, c_i64, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_int, c_int, _P, c_i64,
+                         _P],
     'b200rl_act_bwd': [_P, _P, _P, c_i64, c_int, _P],
     'b200rl_conv2d_fwd': [_P, c_int, c_f32, _P, _P, _P, ctypes.POINTER(ConvGeom), c_int, _P,
                           c_i64, _P],
     'b200rl_conv2d_bwd': [_P, c_int, c_f32, _P, _P, _P, _P, _P, ctypes.POINTER(ConvGeom), c_int,
-                          _P, c_i64, _P],
+                          c_int, _P, c_i64, _P],
     'b200rl_adam_tf': [_P, _P, _P, _P, c_i64, c_f32, c_f32, c_f32, c_f32, _P, _P, _P],
     'b200rl_rmsprop_tf': [_P, _P, _P, _P, _P, c_i64, c_f32, c_f32, c_f32, c_f32, c_int, _P, _P],
     'b200rl_soft_update': [_P, _P, c_i64, c_f32, c_i64, _P, _P],
@@ -114,6 +124,7 @@ _RESTYPES = {
     'b200rl_last_error': ctypes.c_char_p,
     'b200rl_version': c_int,
     'b200rl_launch_count': c_i64,
+    'b200rl_get_pdl': c_int,
 }
 
 _lib = None

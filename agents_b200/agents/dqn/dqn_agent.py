@@ -52,7 +52,8 @@ def _loss_kind(fn):
 class DqnAgent(tf_agent.TFAgent):
   """A DQN agent (Mnih et al. 2015) with n-step updates."""
 
-  _DOUBLE_Q = False
+  _DOUBLE_Q = False          # select the bootstrap action with the online network
+  _SELECT_UNMASKED = False   # D3qn: raw argmax over the selector's output (no action constraints)
 
   def __init__(self, time_step_spec, action_spec, q_network, optimizer,
                observation_and_action_constraint_splitter=None, epsilon_greedy=0.1,
@@ -183,9 +184,15 @@ class DqnAgent(tf_agent.TFAgent):
     with torch.cuda.stream(side if side is not None else main), \
         workspace.slot(1 if side is not None else 0):
       next_t, _ = self._target_q_network(obsn)
+      if isinstance(next_t, tuple):                # dueling nets may emit (q, ...) (:723-726)
+        next_t = next_t[0]
       next_sel = next_t
       if self._DOUBLE_Q:
         next_sel, _ = self._q_network(obsn)        # DdqnAgent (dqn_agent.py:686-688)
+        if isinstance(next_sel, tuple):            # D3qnAgent reads element 1 (:730)
+          next_sel = next_sel[1] if self._SELECT_UNMASKED else next_sel[0]
+    if self._SELECT_UNMASKED:
+      next_mask = None                             # tf.math.argmax on the raw values (:731)
     if keep_tape:
       q, tape = self._q_network.forward_train(obs0)
     else:
@@ -260,3 +267,16 @@ class DqnAgent(tf_agent.TFAgent):
 class DdqnAgent(DqnAgent):
   """Double DQN (van Hasselt et al. 2015; dqn_agent.py:649-700)."""
   _DOUBLE_Q = True
+
+
+class D3qnAgent(DqnAgent):
+  """Double Dueling DQN (Wang et al. 2016; dqn_agent.py:704-753).
+
+  Like DdqnAgent the bootstrap action comes from the ONLINE network evaluated at s_n, but it is
+  a plain `tf.math.argmax` of that output (:731) -- it does not go through the greedy policy, so
+  an `observation_and_action_constraint_splitter` mask is NOT applied to the selection (the
+  reference's masked-action test expects 26.0 for this agent and 23.75 for the other two,
+  dqn_agent_test.py:556).  The value is still read from the target network (:737-741).
+  """
+  _DOUBLE_Q = True
+  _SELECT_UNMASKED = True

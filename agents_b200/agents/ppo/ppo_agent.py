@@ -5,8 +5,9 @@ Drop-in for `tf_agents.agents.ppo.ppo_agent.PPOAgent` restricted to what PPOClip
 surrogate, value loss (optionally clipped), entropy bonus, L2 regularisation, GAE / TD-lambda
 returns, advantage normalisation, observation / reward normalisers, `num_epochs` full-batch
 updates per `train` call with global-norm clipping and ONE optimiser over actor + value
-parameters.  The adaptive-KL penalty terms (ppo_agent.py:1514-1690) are zeroed by PPOClipAgent
-(ppo_clip_agent.py:226-232) and are not implemented: non-zero KL settings raise.
+parameters, and the KL penalty of the original formulation (ppo_agent.py:1514-1690): squared
+KL-cutoff loss + adaptive-beta loss inside every epoch, beta updated once after the epochs.
+PPOClipAgent sets both to zero (ppo_clip_agent.py:226-232) and skips that work entirely.
 
 Device work of `train(experience[B, T])` (csrc/ppo.cu, scans.cu, nn.cu, optim.cu):
   value net on B*T observations -> gamma*d*episode_mask -> returns scan -> GAE scan (warp-shuffle
@@ -15,6 +16,7 @@ Device work of `train(experience[B, T])` (csrc/ppo.cu, scans.cu, nn.cu, optim.cu
   loss with gradients, backward, global-norm scale, fused Adam on the joint flat buffer.
 """
 import collections
+import ctypes
 
 import torch
 
@@ -51,11 +53,6 @@ class PPOAgent(tf_agent.TFAgent):
                name=None, seed=0):
     if actor_net is None or value_net is None:
       raise ValueError('actor_net and value_net must be given.')
-    if initial_adaptive_kl_beta != 0.0 or kl_cutoff_factor != 0.0:
-      raise NotImplementedError(
-          'The adaptive-KL / KL-cutoff penalties (ppo_agent.py:1514-1690) are outside the hot '
-          'path; use PPOClipAgent (which sets them to zero) or pass initial_adaptive_kl_beta=0, '
-          'kl_cutoff_factor=0.')
     if not use_gae:
       raise NotImplementedError('Only use_gae=True is supported (PPO examples use GAE).')
     if shared_vars_l2_reg:
@@ -71,6 +68,18 @@ class PPOAgent(tf_agent.TFAgent):
     self._entropy_regularization = entropy_regularization
     self._policy_l2_reg, self._value_function_l2_reg = policy_l2_reg, value_function_l2_reg
     self._value_pred_loss_coef = value_pred_loss_coef
+    # KL penalty configuration (ppo_agent.py:319-345); beta is a device-resident variable
+    self._kl_cutoff_factor = float(kl_cutoff_factor)
+    self._kl_cutoff_coef = float(kl_cutoff_coef)
+    self._initial_adaptive_kl_beta = float(initial_adaptive_kl_beta)
+    self._adaptive_kl_target = float(adaptive_kl_target)
+    self._adaptive_kl_tolerance = float(adaptive_kl_tolerance)
+    self._adaptive_kl_beta = None
+    if initial_adaptive_kl_beta > 0.0:
+      self._adaptive_kl_beta = torch.full((1,), float(initial_adaptive_kl_beta),
+                                          dtype=torch.float32, device=device)
+    self._kl_mean = torch.zeros(1, dtype=torch.float32, device=device)
+    self._kl_terms = torch.zeros(3, dtype=torch.float32, device=device)
     self._num_epochs = num_epochs
     self._use_td_lambda_return = use_td_lambda_return
     self._reward_norm_clipping = reward_norm_clipping
@@ -111,6 +120,7 @@ class PPOAgent(tf_agent.TFAgent):
     self.replicas = 1
     self._grad_sync = None       # callable(flat_grads) for data-parallel runs (train.Learner)
     self._stat_sync = None       # callable(tensor) SUM-all-reduce of small statistics
+    self._replica_rank = 0       # this process's index among `replicas` (set by train.Learner)
 
   @property
   def actor_net(self):
@@ -209,25 +219,29 @@ class PPOAgent(tf_agent.TFAgent):
     old_logp = torch.empty(N, dtype=torch.float32, device=dev)
     _lib.call('b200rl_normal_logp', _lib.ptr(old_loc), _lib.ptr(old_scale), A, _lib.ptr(action), N,
               A, _lib.ptr(old_logp), st)
-    # _normalize_advantages over axes (0, 1), unmasked (:893-895, :100-110)
+    # _normalize_advantages over axes (0, 1), unmasked (:893-895, :100-110); sharded runs merge
+    # the per-rank moments with one collective (tensor_normalizer.batch_moments)
     mean = torch.empty(1, dtype=torch.float32, device=dev)
     var = torch.empty(1, dtype=torch.float32, device=dev)
     n_glob = float(N * self.replicas)
-    _lib.call('b200rl_colsum', _lib.ptr(adv), None, 0, N, 1, 1.0 / n_glob, _lib.ptr(mean),
-              _lib.ptr(ws), nb, st)
-    if self._stat_sync is not None:
-      self._stat_sync(mean)
-    _lib.call('b200rl_colsum', _lib.ptr(adv), _lib.ptr(mean), 1, N, 1, 1.0 / n_glob, _lib.ptr(var),
-              _lib.ptr(ws), nb, st)
-    if self._stat_sync is not None:
-      self._stat_sync(var)
+    tensor_normalizer.batch_moments(adv.reshape(N, 1), 1, mean, var, self._stat_sync,
+                                    self.replicas, self._replica_rank)
+    var.mul_(1.0 / n_glob)                                         # m2 -> population variance
     adv_n = torch.empty(N, dtype=torch.float32, device=dev)
     _lib.call('b200rl_normalize', _lib.ptr(adv), _lib.ptr(adv_n), N, 1, _lib.ptr(mean),
               _lib.ptr(var), None, 1e-8, 0.0, st)
     obs_n = obs
     if self._observation_normalizer is not None:
       obs_n = self._observation_normalizer.normalize(obs)
-    losses = torch.empty(5, dtype=torch.float32, device=dev)
+    losses = torch.empty(6, dtype=torch.float32, device=dev)
+    use_kl = not (self._initial_adaptive_kl_beta == 0 and self._kl_cutoff_factor == 0)  # :586
+    kl_arg = None
+    if use_kl:
+      # mean_kl is the mean over the GLOBAL batch (per-rank partial sums are SUM-reduced) and the
+      # KL gradient carries 1/N_global, so R replicas reproduce the one-device update on the
+      # concatenated batch (the reference's per-replica reduce_mean would weigh the penalty R x).
+      kl_arg = _lib.PpoKl(_lib.ptr(old_loc), _lib.ptr(old_scale), A, _lib.ptr(self._kl_terms),
+                          1.0 / n_glob)
     l2 = torch.zeros(1, dtype=torch.float32, device=dev)
     dloc = torch.empty((N, A), dtype=torch.float32, device=dev)
     dscale = torch.empty((N, A), dtype=torch.float32, device=dev)
@@ -236,13 +250,17 @@ class PPOAgent(tf_agent.TFAgent):
     for _ in range(self._num_epochs):                             # :925-967
       (loc, scale), actx = self._actor_net.forward_train(obs_n)
       v, vtape = self._value_net.forward_train(obs_n)
+      if use_kl:
+        self._mean_kl(loc, scale, old_loc, old_scale, w, N, A, n_glob)
+        self._kl_penalty_terms()
       _lib.call('b200rl_ppo_loss', _lib.ptr(loc), _lib.ptr(scale), A, _lib.ptr(action),
                 _lib.ptr(old_logp), _lib.ptr(adv_n), _lib.ptr(returns), _lib.ptr(v), _lib.ptr(vp),
                 _lib.ptr(w), N, A, T, gb, float(self._importance_ratio_clipping),
                 float(self._value_clipping), float(self._value_pred_loss_coef),
                 float(self._entropy_regularization), float(self._log_prob_clipping),
                 _lib.ptr(losses), _lib.ptr(dloc), _lib.ptr(dscale), A, _lib.ptr(dv),
-                _lib.ptr(self._nan_flag), _lib.ptr(ws), nb, st)
+                _lib.ptr(self._nan_flag), ctypes.byref(kl_arg) if use_kl else None, _lib.ptr(ws),
+                nb, st)
       self._actor_net.backward(actx, (dloc, dscale))
       self._value_net.backward(vtape, dv)
       l2.zero_()
@@ -257,15 +275,84 @@ class PPOAgent(tf_agent.TFAgent):
         scale_dev = self._scale_dev
       self._optimizer.apply_flat(self._flat_params, self._flat_grads, scale_dev)
       self._bump_train_step(1)
+    if self._initial_adaptive_kl_beta > 0:                        # :978-989
+      loc, scale = self._actor_net.distribution_params(obs_n)
+      self._mean_kl(loc, scale, old_loc, old_scale, w, N, A, n_glob)
+      self._update_beta()
     if self.update_normalizers_in_train:                          # :991-993
       self.update_observation_normalizer(obs)
       self.update_reward_normalizer(experience.reward)
     zero = torch.zeros((), dtype=torch.float32, device=dev)
     extra = PPOLossInfo(policy_gradient_loss=losses[0], value_estimation_loss=losses[1],
                         l2_regularization_loss=l2.reshape(()),
-                        entropy_regularization_loss=losses[2], kl_penalty_loss=zero,
-                        clip_fraction=losses[3])
+                        entropy_regularization_loss=losses[2],
+                        kl_penalty_loss=losses[5] if use_kl else zero, clip_fraction=losses[3])
     return tf_agent.LossInfo(losses[4] + l2.reshape(()), extra)
+
+  # ---- KL penalty (ppo_agent.py:1514-1690) ------------------------------------------------------
+  def _mean_kl(self, loc, scale, old_loc, old_scale, w, N, A, n_glob, out_kl=None):
+    """self._kl_mean <- sum_n w_n KL(old_n || new_n) / N_global (all-reduced when sharded)."""
+    ws, nb = workspace.get(loc.device)
+    _lib.call('b200rl_ppo_kl', _lib.ptr(loc), _lib.ptr(scale), A, _lib.ptr(old_loc),
+              _lib.ptr(old_scale), A, _lib.ptr(w), N, A, 1.0 / n_glob, _lib.ptr(out_kl),
+              _lib.ptr(self._kl_mean), _lib.ptr(ws), nb, _lib.stream())
+    if self._stat_sync is not None:
+      self._stat_sync(self._kl_mean)
+
+  def _kl_penalty_terms(self):
+    _lib.call('b200rl_ppo_kl_terms', _lib.ptr(self._kl_mean), _lib.ptr(self._adaptive_kl_beta),
+              self._kl_cutoff_factor, self._adaptive_kl_target, self._kl_cutoff_coef,
+              _lib.ptr(self._kl_terms), _lib.stream())
+
+  def _update_beta(self):
+    _lib.call('b200rl_ppo_kl_beta_update', _lib.ptr(self._kl_mean),
+              _lib.ptr(self._adaptive_kl_beta), self._adaptive_kl_target,
+              self._adaptive_kl_tolerance, _lib.stream())
+
+  def _set_mean_kl(self, kl_divergence):
+    kl = torch.as_tensor(kl_divergence, dtype=torch.float32, device=self._kl_mean.device)
+    kl = kl.reshape(-1).contiguous()
+    ws, nb = workspace.get(kl.device)
+    _lib.call('b200rl_colsum', _lib.ptr(kl), None, 0, kl.numel(), 1, 1.0 / kl.numel(),
+              _lib.ptr(self._kl_mean), _lib.ptr(ws), nb, _lib.stream())
+
+  def kl_cutoff_loss(self, kl_divergence, debug_summaries=False):
+    """coef * max(mean(kl) - factor * target, 0)^2 (ppo_agent.py:1514-1539)."""
+    self._set_mean_kl(kl_divergence)
+    self._kl_penalty_terms()
+    return self._kl_terms[0].clone()
+
+  def adaptive_kl_loss(self, kl_divergence, debug_summaries=False):
+    """beta * mean(kl) (ppo_agent.py:1541-1558)."""
+    self._set_mean_kl(kl_divergence)
+    self._kl_penalty_terms()
+    return self._kl_terms[1].clone()
+
+  def update_adaptive_kl_beta(self, kl_divergence):
+    """beta <- clip(beta * {1/1.5, 1, 1.5}) depending on mean(kl) vs target*(1 -/+ tolerance)
+    (ppo_agent.py:1632-1675); returns beta."""
+    if self._adaptive_kl_beta is None:
+      return None
+    self._set_mean_kl(kl_divergence)
+    self._update_beta()
+    return self._adaptive_kl_beta[0].clone()
+
+  def kl_penalty_loss(self, time_steps, action_distribution_parameters,
+                      current_policy_distribution, weights, debug_summaries=False):
+    """kl_cutoff_loss + adaptive_kl_loss of weights * KL(old || current) (:1586-1630).
+    `current_policy_distribution` is a (loc, scale) pair of [N, A] tensors."""
+    loc, scale = current_policy_distribution
+    old_loc = action_distribution_parameters['loc'].float()
+    old_scale = action_distribution_parameters['scale'].float()
+    A = loc.shape[-1]
+    loc, scale = loc.reshape(-1, A).contiguous(), scale.reshape(-1, A).contiguous()
+    old_loc, old_scale = old_loc.reshape(-1, A).contiguous(), old_scale.reshape(-1, A).contiguous()
+    N = loc.shape[0]
+    w = torch.as_tensor(weights, dtype=torch.float32, device=loc.device).reshape(-1).contiguous()
+    kl = torch.empty(N, dtype=torch.float32, device=loc.device)
+    self._mean_kl(loc, scale, old_loc, old_scale, w, N, A, float(N * self.replicas), out_kl=kl)
+    # through the public methods, like the reference (its test mocks them)
+    return self.kl_cutoff_loss(kl, debug_summaries) + self.adaptive_kl_loss(kl, debug_summaries)
 
   def _l2_regularization(self, l2_accum):
     """l2_regularization_loss (:1088-1157): coef * sum(kernel^2) over kernels (not biases);
@@ -285,11 +372,13 @@ class PPOAgent(tf_agent.TFAgent):
 
   def update_observation_normalizer(self, batched_observations):
     if self._observation_normalizer is not None:
-      self._observation_normalizer.update(batched_observations)
+      self._observation_normalizer.update(batched_observations, stat_sync=self._stat_sync,
+                                          replicas=self.replicas, rank=self._replica_rank)
 
   def update_reward_normalizer(self, batched_rewards):
     if self._reward_normalizer is not None:
-      self._reward_normalizer.update(batched_rewards)
+      self._reward_normalizer.update(batched_rewards, stat_sync=self._stat_sync,
+                                     replicas=self.replicas, rank=self._replica_rank)
 
   def check_numerics(self):
     if int(self._nan_flag.item()) != 0:

@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(256) dqn_td_loss_kernel(
     float gamma_pow, float reward_scale, int loss_kind, float global_batch,
     float* __restrict__ loss, float* __restrict__ td_loss, float* __restrict__ td_error,
     float* __restrict__ dq, int32_t* __restrict__ nan_flag) {
+  pdl_prologue();
   __shared__ float red[32];
   float partial = 0.f;
   const int64_t n = T - 1;
@@ -109,10 +110,7 @@ extern "C" int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt,
   B200RL_CHECK_ARG(loss_kind == B200RL_LOSS_HUBER || loss_kind == B200RL_LOSS_SQUARED,
                    "dqn_td_loss: unknown loss kind %d", loss_kind);
   B200RL_CHECK_ARG(global_batch > 0.f, "dqn_td_loss: global_batch must be > 0");
-  dqn_td_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
-      q, next_q_tgt, next_q_sel, next_mask, actions, step_type0, traj_reward, traj_discount,
-      weights, B, A, T, (float)gamma, (float)pow(gamma, (double)(T - 2)), (float)reward_scale,
-      loss_kind, global_batch, loss, td_loss, td_error, dq, nan_flag);
+  B200RL_LAUNCH(dqn_td_loss_kernel, 1, 256, 0, (cudaStream_t)stream, q, next_q_tgt, next_q_sel, next_mask, actions, step_type0, traj_reward, traj_discount, weights, B, A, T, (float)gamma, (float)pow(gamma, (double)(T - 2)), (float)reward_scale, loss_kind, global_batch, loss, td_loss, td_error, dq, nan_flag);
   B200RL_CHECK_LAUNCH("dqn_td_loss");
   return B200RL_OK;
 }

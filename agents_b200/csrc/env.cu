@@ -35,6 +35,7 @@ __global__ void __launch_bounds__(256) eps_greedy_kernel(const float* __restrict
                                                          const float* __restrict__ u_in,
                                                          const int32_t* __restrict__ rand_in,
                                                          int32_t* __restrict__ out) {
+  pdl_prologue();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     // greedy: Categorical(logits).mode() == first argmax; masked logits -> dtype.min
@@ -77,6 +78,7 @@ __global__ void __launch_bounds__(256) env_random_step_kernel(
     int32_t* __restrict__ step_type, int32_t* __restrict__ out_step_type, void* __restrict__ obs,
     int64_t obs_elems, int obs_is_u8, float* __restrict__ reward, float* __restrict__ discount,
     int64_t B, float p_term, uint64_t seed, uint64_t* rng_call) {
+  pdl_prologue();
   const int64_t b = blockIdx.y;
   const uint64_t call = rng_call[0];
   const int64_t vec_per_env = obs_is_u8 ? (obs_elems + 15) / 16 : (obs_elems + 3) / 4;
@@ -124,6 +126,7 @@ __global__ void __launch_bounds__(256) env_cartpole_step_kernel(
     const int32_t* __restrict__ action, float* __restrict__ obs, float* __restrict__ reward,
     float* __restrict__ discount, int64_t B, int32_t max_steps, uint64_t seed,
     uint64_t* rng_call) {
+  pdl_prologue();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b < B) {
     float x = state[b * 4 + 0], xd = state[b * 4 + 1], th = state[b * 4 + 2], thd = state[b * 4 + 3];
@@ -178,8 +181,7 @@ int b200rl_epsilon_greedy(const float* q, const int32_t* mask, int64_t B, int64_
   B200RL_CHECK_ARG((u_dev == nullptr) == (rand_dev == nullptr),
                    "epsilon_greedy: u and rand must both be given or both NULL");
   B200RL_CHECK_ARG(u_dev || rng_call_dev, "epsilon_greedy: need rng_call_dev");
-  eps_greedy_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      q, mask, B, A, eps, seed, rng_call_dev, u_dev, rand_dev, out_action);
+  B200RL_LAUNCH(eps_greedy_kernel, (unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream, q, mask, B, A, eps, seed, rng_call_dev, u_dev, rand_dev, out_action);
   B200RL_CHECK_LAUNCH("epsilon_greedy");
   return B200RL_OK;
 }
@@ -194,9 +196,7 @@ int b200rl_env_random_step(int32_t* step_type, int32_t* out_step_type, void* obs
   B200RL_CHECK_ARG(B <= 65535, "env_random_step: B too large for grid.y");
   const int64_t vec = obs_is_u8 ? (obs_elems + 15) / 16 : (obs_elems + 3) / 4;
   dim3 grid((unsigned)((vec + 255) / 256), (unsigned)B);
-  env_random_step_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
-      step_type, out_step_type, obs, obs_elems, obs_is_u8, reward, discount, B, p_term, seed,
-      rng_call_dev);
+  B200RL_LAUNCH(env_random_step_kernel, grid, 256, 0, (cudaStream_t)stream, step_type, out_step_type, obs, obs_elems, obs_is_u8, reward, discount, B, p_term, seed, rng_call_dev);
   B200RL_CHECK_LAUNCH("env_random_step");
   return B200RL_OK;
 }
@@ -208,8 +208,7 @@ int b200rl_env_cartpole_step(float* state, int32_t* steps, int32_t* step_type,
   B200RL_CHECK_ARG(state && steps && step_type && action && obs && reward && discount &&
                        rng_call_dev && B >= 1,
                    "env_cartpole_step: bad argument");
-  env_cartpole_step_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      state, steps, step_type, action, obs, reward, discount, B, max_steps, seed, rng_call_dev);
+  B200RL_LAUNCH(env_cartpole_step_kernel, (unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream, state, steps, step_type, action, obs, reward, discount, B, max_steps, seed, rng_call_dev);
   B200RL_CHECK_LAUNCH("env_cartpole_step");
   return B200RL_OK;
 }

@@ -21,6 +21,7 @@ __global__ void __launch_bounds__(256) frame_stack_gather_kernel(
     const uint8_t* __restrict__ frames, const int32_t* __restrict__ step_type, int64_t frame_bytes,
     int64_t L, const int64_t* __restrict__ ids, const int64_t* __restrict__ offs, int64_t T,
     uint8_t* __restrict__ out) {
+  pdl_prologue();
   __shared__ int64_t src_row[K];
   const int64_t row = blockIdx.x;                    // b * T + t
   const int64_t b = row / T, t = row - b * T;
@@ -86,10 +87,10 @@ extern "C" int b200rl_rb_gather_frame_stack(const void* frames, const int32_t* s
   const uint8_t* fr = (const uint8_t*)frames;
   uint8_t* o = (uint8_t*)out;
   switch (K) {
-    case 1: frame_stack_gather_kernel<1><<<grid, 256, 0, st>>>(fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
-    case 2: frame_stack_gather_kernel<2><<<grid, 256, 0, st>>>(fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
-    case 3: frame_stack_gather_kernel<3><<<grid, 256, 0, st>>>(fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
-    default: frame_stack_gather_kernel<4><<<grid, 256, 0, st>>>(fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
+    case 1: B200RL_LAUNCH(frame_stack_gather_kernel<1>, grid, 256, 0, st, fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
+    case 2: B200RL_LAUNCH(frame_stack_gather_kernel<2>, grid, 256, 0, st, fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
+    case 3: B200RL_LAUNCH(frame_stack_gather_kernel<3>, grid, 256, 0, st, fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
+    default: B200RL_LAUNCH(frame_stack_gather_kernel<4>, grid, 256, 0, st, fr, step_type, frame_bytes, max_length, ids_dev, offsets_dev, T, o); break;
   }
   B200RL_CHECK_LAUNCH("gather_frame_stack");
   return B200RL_OK;

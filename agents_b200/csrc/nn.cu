@@ -224,6 +224,20 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
+// Input-gradient mask: when the GEMM input X is the OUTPUT of an activation (the previous layer
+// of the stack), dLoss/dX is multiplied by act'(X) on its way out, so the caller receives the
+// gradient w.r.t. that layer's pre-activation and the separate act_bwd pass disappears.
+struct ActMask {
+  const float* y = nullptr;   // X as produced by the previous layer (nullptr: no mask)
+  int64_t ld = 0;             // dense: row stride of y; conv: elements between images
+  int act = 0;
+};
+__device__ __forceinline__ float dact(float y, float g, int act) {
+  if (act == B200RL_ACT_RELU) return y > 0.f ? g : 0.f;
+  if (act == B200RL_ACT_TANH) return g * (1.f - y * y);
+  return g;
+}
+
 }  // namespace b200rl
 #include "tc_gemm.cuh"
 namespace b200rl {
@@ -236,7 +250,8 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const AL a, const BL b, floa
                                                     const float* __restrict__ bias, int64_t M,
                                                     int64_t N, int64_t K, int act, int beta,
                                                     int splits, int64_t k_per_split,
-                                                    float* __restrict__ ws) {
+                                                    float* __restrict__ ws, const ActMask mask) {
+  pdl_prologue();
   static_assert((BM / TM) * (BN / TN) == 256, "thread grid must be 256");
   constexpr int TX = BN / TN;
   constexpr int GM = TM >= 4 ? 4 : TM, GN = TN >= 4 ? 4 : TN;  // contiguous group widths
@@ -340,6 +355,7 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const AL a, const BL b, floa
           if (splits == 1) {
             if (bias) v += bias[n];
             v = apply_act(v, act);
+            if (mask.y) v = dact(mask.y[m * mask.ld + n], v, mask.act);
             if (beta) v += out[m * N + n];
           }
           out[m * N + n] = v;
@@ -349,13 +365,15 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const AL a, const BL b, floa
 
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __restrict__ C,
                                      const float* __restrict__ bias, int64_t MN, int64_t N,
-                                     int splits, int act, int beta) {
+                                     int splits, int act, int beta, const ActMask mask) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= MN) return;
   float v = 0.f;
   for (int s = 0; s < splits; ++s) v += ws[(int64_t)s * MN + i];
   if (bias) v += bias[i % N];
   v = apply_act(v, act);
+  if (mask.y) v = dact(mask.y[(i / N) * mask.ld + i % N], v, mask.act);
   if (beta) v += C[i];
   C[i] = v;
 }
@@ -363,6 +381,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
 // dZ = dY * act'(Y)
 __global__ void act_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dY,
                                float* __restrict__ dZ, int64_t n, int act) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float y = Y[i], g = dY[i];
@@ -380,6 +399,7 @@ constexpr int kColRows = 512;  // rows per partial block
 __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __restrict__ dZ,
                                                              float* __restrict__ part, int64_t M,
                                                              int64_t N) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int64_t n = (int64_t)blockIdx.x * 32 + lane;
@@ -402,6 +422,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const float* __rest
 __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restrict__ part,
                                                            float* __restrict__ db, int64_t nparts,
                                                            int64_t N, int beta) {
+  pdl_prologue();
   // one warp per column: lanes stride over the partials, fixed-order shuffle reduction
   const int lane = threadIdx.x & 31;
   const int64_t n = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -414,7 +435,8 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
 
 // col2im in gather form (deterministic): dX[n,y,x,c] = sum over kernel taps hitting (y,x).
 __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict__ dX, ConvGeom g,
-                              int64_t total, int Kc) {
+                              int64_t total, int Kc, const ActMask mask) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % g.C);
@@ -434,6 +456,7 @@ __global__ void col2im_kernel(const float* __restrict__ dcol, float* __restrict_
       s += dcol[pos * Kc + (ky * g.KW + kx) * g.C + c];
     }
   }
+  if (mask.y) s = dact(mask.y[n * mask.ld + ((int64_t)y * g.W + x) * g.C + c], s, mask.act);
   dX[i] = s;
 }
 
@@ -449,6 +472,7 @@ struct GemmArgs {
   int64_t ws_bytes;
   cudaStream_t st;
   float out_scale = 1.f;  // tensor-core path only: multiplies the accumulator (raw-u8 operands)
+  ActMask mask{};         // input-gradient GEMMs: multiply the result by act'(mask.y)
 };
 
 template <int BM, int BN, int TM, int TN, class AL, class BL>
@@ -473,19 +497,26 @@ static int launch_gemm_cfg(const AL& a, const BL& b, const GemmArgs& g) {
   if (splits < 1) splits = 1;
   B200RL_CHECK_ARG(tm <= 65535, "gemm: M too large for grid.y (%lld tiles)", (long long)tm);
   dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
-  sgemm_kernel<BM, BN, TM, TN, AL, BL><<<grid, 256, 0, g.st>>>(
-      a, b, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws);
+  B200RL_LAUNCH((sgemm_kernel<BM, BN, TM, TN, AL, BL>), grid, 256, 0, g.st, a, b, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.mask);
   B200RL_CHECK_LAUNCH("sgemm");
   if (splits > 1) {
     const int64_t MN = g.M * g.N;
-    splitk_reduce_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, g.st>>>(
-        (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta);
+    B200RL_LAUNCH(splitk_reduce_kernel, (unsigned)((MN + 255) / 256), 256, 0, g.st, (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta, g.mask);
     B200RL_CHECK_LAUNCH("splitk_reduce");
   }
   return B200RL_OK;
 }
 
 // 0 = fp32 FFMA (sgemm_kernel), 1 = tcgen05 3xTF32, 2 = tcgen05 single-pass TF32 (not 1e-5 safe)
+// B200RL_FUSE_BIAS_GRAD=0 keeps the separate column-sum kernels (A/B switch for profiles/)
+static int fuse_bias_grad() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200RL_FUSE_BIAS_GRAD");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
 static int g_gemm_mode = -1;
 static int gemm_mode() {
   if (g_gemm_mode < 0) {
@@ -528,13 +559,11 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
   if (splits < 1) splits = 1;
   B200RL_CHECK_ARG(tm <= 65535, "tc_gemm: M too large for grid.y (%lld tiles)", (long long)tm);
   dim3 grid((unsigned)tn, (unsigned)tm, (unsigned)splits);
-  kernel<<<grid, tc::kThreads, L::kBytes, g.st>>>(a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act,
-                                                  g.beta, splits, kps, (float*)g.ws, g.out_scale);
+  B200RL_LAUNCH(kernel, grid, tc::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale);
   B200RL_CHECK_LAUNCH("tc_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
-    splitk_reduce_kernel<<<(unsigned)((MN + 255) / 256), 256, 0, g.st>>>(
-        (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta);
+    B200RL_LAUNCH(splitk_reduce_kernel, (unsigned)((MN + 255) / 256), 256, 0, g.st, (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta, g.mask);
     B200RL_CHECK_LAUNCH("splitk_reduce");
   }
   return B200RL_OK;
@@ -542,7 +571,9 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
 
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
-  const tc::EpiArgs none{};
+  tc::EpiArgs none{};
+  none.mask = g.mask;
+  B200RL_CHECK_ARG(!(g.mask.y && g.beta), "gemm: an input-gradient mask cannot be combined with accumulation");
   if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), PASSES, tc::EPI_STORE>(a, b, g, none);  // <= 96 KB -> 2 CTAs/SM
   if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 96 KB -> 2 CTAs/SM
   return launch_tc_cfg<128, 3, PASSES, tc::EPI_STORE>(a, b, g, none);
@@ -551,8 +582,12 @@ static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
 // Weight-gradient GEMMs (no bias / activation): in tensor-core mode the split-K partials are
 // accumulated with red.global.add straight into the (zeroed) gradient instead of going through
 // a workspace + reduce kernel.  Summation order across splits is not fixed.
+// `db` (optional): bias gradient = column sums of B; when the tensor-core path takes the GEMM and
+// B is an MN-major view the sums are accumulated by the producers of the same kernel and
+// *db_fused is set, otherwise the caller runs the separate column-sum kernels.
 template <class AL, class BL>
-static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g);
+static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g, float* db = nullptr,
+                            bool* db_fused = nullptr);
 
 template <class AL, class BL>
 static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
@@ -575,18 +610,25 @@ static int launch_gemm(const AL& a, const BL& b, const GemmArgs& g) {
 }
 
 template <class AL, class BL>
-static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g) {
+static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g, float* db, bool* db_fused) {
   const int mode = gemm_mode();
+  if (db_fused) *db_fused = false;
   if (mode == 0 || g.N < 16 || g.M < 32 || g.K < 8 || g.bias != nullptr || g.act != B200RL_ACT_NONE)
     return launch_gemm(a, b, g);
+  const bool fuse_db = db != nullptr && !BL::kKContig && fuse_bias_grad();
   if (!g.beta) {
     cudaError_t e = cudaMemsetAsync(g.C, 0, (size_t)(g.M * g.N) * sizeof(float), g.st);
+    if (e == cudaSuccess && fuse_db) e = cudaMemsetAsync(db, 0, (size_t)g.N * sizeof(float), g.st);
     if (e != cudaSuccess) {
       set_error("grad gemm: memset failed: %s", cudaGetErrorString(e));
       return B200RL_ERR_CUDA;
     }
   }
-  const tc::EpiArgs none{};
+  tc::EpiArgs none{};
+  if (fuse_db) {
+    none.colsum = db;
+    if (db_fused) *db_fused = true;
+  }
   if (mode == 2) {
     if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), 1, tc::EPI_ATOMIC>(a, b, g, none);
     if (g.N <= 64) return launch_tc_cfg<64, 2, 1, tc::EPI_ATOMIC>(a, b, g, none);
@@ -605,9 +647,9 @@ static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, vo
                    (long long)(nparts * N * sizeof(float)));
   B200RL_CHECK_ARG(nparts <= 65535, "bias gradient: too many rows");
   dim3 grid((unsigned)((N + 31) / 32), (unsigned)nparts);
-  colsum_partial_kernel<<<grid, 256, 0, st>>>(dZ, (float*)ws, M, N);
+  B200RL_LAUNCH(colsum_partial_kernel, grid, 256, 0, st, dZ, (float*)ws, M, N);
   B200RL_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>((const float*)ws, db, nparts, N, beta);
+  B200RL_LAUNCH(colsum_final_kernel, (unsigned)((N + 7) / 8), 256, 0, st, (const float*)ws, db, nparts, N, beta);
   B200RL_CHECK_LAUNCH("colsum_final");
   return B200RL_OK;
 }
@@ -674,22 +716,25 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
 
 int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
                      float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
-                     void* workspace, int64_t ws_bytes, void* stream) {
+                     int x_act, void* workspace, int64_t ws_bytes, void* stream) {
   B200RL_CHECK_ARG(X && W && dY, "dense_bwd: NULL argument");
   B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_bwd: ldx < K");
+  B200RL_CHECK_ARG(x_act >= B200RL_ACT_NONE && x_act <= B200RL_ACT_TANH, "dense_bwd: x_act");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (dX) {
     GemmArgs g{dX, nullptr, M, K, N, B200RL_ACT_NONE, 0, workspace, ws_bytes, st};
+    if (x_act != B200RL_ACT_NONE) g.mask = ActMask{X, ldx ? ldx : K, x_act};
     rc = launch_gemm(ARow{dY, N}, BCol{W, N}, g);
     if (rc) return rc;
   }
+  bool db_fused = false;
   if (dW) {
     GemmArgs g{dW, nullptr, K, N, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
-    rc = launch_grad_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g);
+    rc = launch_grad_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g, db, &db_fused);
     if (rc) return rc;
   }
-  if (db) {
+  if (db && !db_fused) {
     rc = colsum(dY, db, M, N, accumulate, workspace, ws_bytes, st);
     if (rc) return rc;
   }
@@ -700,7 +745,7 @@ int b200rl_act_bwd(const float* Y, const float* dY, float* dZ, int64_t n, int ac
                    void* stream) {
   B200RL_CHECK_ARG(Y && dY && dZ && n >= 0, "act_bwd: bad argument");
   if (n == 0) return B200RL_OK;
-  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Y, dY, dZ, n, act);
+  B200RL_LAUNCH(act_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, Y, dY, dZ, n, act);
   B200RL_CHECK_LAUNCH("act_bwd");
   return B200RL_OK;
 }
@@ -729,32 +774,36 @@ int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt
 
 int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
                       const float* dY, float* dX, float* dW, float* db,
-                      const b200rl_conv_t* c, int accumulate, void* workspace,
+                      const b200rl_conv_t* c, int accumulate, int x_act, void* workspace,
                       int64_t ws_bytes, void* stream) {
   B200RL_CHECK_ARG(X && Wt && dY, "conv2d_bwd: NULL argument");
   B200RL_CHECK_ARG(!(dX && x_is_u8), "conv2d_bwd: no input gradient for u8 input");
+  B200RL_CHECK_ARG(x_act >= B200RL_ACT_NONE && x_act <= B200RL_ACT_TANH, "conv2d_bwd: x_act");
   ConvGeom cg;
   int rc = make_geom(c, cg);
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
   const int64_t F = c->F;
+  ActMask mask{};
+  if (x_act != B200RL_ACT_NONE && !x_is_u8) mask = ActMask{(const float*)X, cg.in_img, x_act};
+  bool db_fused = false;
   if (dW) {  // dW[K,F] = im2col(X)^T @ dY
     GemmArgs g{dW, nullptr, K, F, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
     if (x_is_u8 && gemm_mode() == 1 && F >= 16 && K >= 32 && M >= 8) {
       g.out_scale = 1.f / x_scale;
       AConvTU8Raw a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
-      rc = launch_grad_gemm(a, BRow{dY, F}, g);
+      rc = launch_grad_gemm(a, BRow{dY, F}, g, db, &db_fused);
     } else if (x_is_u8) {
       AConvT<uint8_t> a{ConvView<uint8_t>{(const uint8_t*)X, cg, x_scale}};
       rc = launch_gemm(a, BRow{dY, F}, g);
     } else {
       AConvT<float> a{ConvView<float>{(const float*)X, cg, 1.f}};
-      rc = launch_grad_gemm(a, BRow{dY, F}, g);
+      rc = launch_grad_gemm(a, BRow{dY, F}, g, db, &db_fused);
     }
     if (rc) return rc;
   }
-  if (db) {
+  if (db && !db_fused) {
     rc = colsum(dY, db, M, F, accumulate, workspace, ws_bytes, st);
     if (rc) return rc;
   }
@@ -768,6 +817,7 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     }
     GemmArgs g{nullptr, nullptr, M, K, F, B200RL_ACT_NONE, 0, nullptr, 0, st};
     tc::EpiArgs epi{cg, dX};
+    epi.mask = mask;
     if (gemm_mode() == 2) rc = launch_tc_cfg<128, 3, 1, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
     else rc = launch_tc_cfg<128, 3, 3, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
     if (rc) return rc;
@@ -780,8 +830,7 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     rc = launch_gemm(ARow{dY, F}, BCol{Wt, F}, g);
     if (rc) return rc;
     const int64_t total = (int64_t)c->N * c->H * c->W * c->C;
-    col2im_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, dX, cg,
-                                                                   total, (int)K);
+    B200RL_LAUNCH(col2im_kernel, (unsigned)((total + 255) / 256), 256, 0, st, (const float*)workspace, dX, cg, total, (int)K, mask);
     B200RL_CHECK_LAUNCH("col2im");
   }
   return B200RL_OK;

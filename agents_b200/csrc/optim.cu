@@ -31,6 +31,7 @@ __global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ p,
                                                       float* __restrict__ v, int64_t n, float lr,
                                                       float b1, float b2, float eps,
                                                       int64_t* step, const float* grad_scale) {
+  pdl_prologue();
   __shared__ float s_lr_t;
   const int64_t t = step[0] + 1;
   if (threadIdx.x == 0) {
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(256) rmsprop_tf_kernel(float* __restrict__ p,
                                                          float lr, float decay, float momentum,
                                                          float eps, int centered,
                                                          const float* grad_scale) {
+  pdl_prologue();
   const float gs = grad_scale ? *grad_scale : 1.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
@@ -83,6 +85,7 @@ __global__ void __launch_bounds__(256) soft_update_kernel(float* __restrict__ ta
                                                           const float* __restrict__ source,
                                                           int64_t n, float tau, int64_t period,
                                                           int64_t* counter) {
+  pdl_prologue();
   bool fire = true;
   int64_t c = 0;
   if (period > 1) {
@@ -102,6 +105,7 @@ __global__ void __launch_bounds__(256) soft_update_kernel(float* __restrict__ ta
 __global__ void __launch_bounds__(1024) clip_by_norm_segments_kernel(float* __restrict__ g,
                                                                      const int64_t* __restrict__ offs,
                                                                      float max_norm) {
+  pdl_prologue();
   __shared__ float red[32];
   const int64_t b = offs[blockIdx.x], e = offs[blockIdx.x + 1];
   float s = 0.f;
@@ -116,6 +120,7 @@ __global__ void __launch_bounds__(1024) clip_by_norm_segments_kernel(float* __re
 constexpr int kNormBlocks = 296;
 __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restrict__ g, int64_t n,
                                                             float* __restrict__ part) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -127,6 +132,7 @@ __global__ void __launch_bounds__(256) sumsq_partial_kernel(const float* __restr
 __global__ void __launch_bounds__(512) global_norm_final_kernel(const float* __restrict__ part,
                                                                 int nparts, float clip,
                                                                 float* scale, float* norm) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = (threadIdx.x < nparts) ? part[threadIdx.x] : 0.f;
   s = block_sum(s, red);
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(512) global_norm_final_kernel(const float* __r
 
 __global__ void add_scaled_kernel(float* __restrict__ dst, const float* __restrict__ src,
                                   int64_t n, float alpha) {
+  pdl_prologue();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = dst[i] + alpha * src[i];
@@ -147,6 +154,7 @@ __global__ void add_scaled_kernel(float* __restrict__ dst, const float* __restri
 
 __global__ void __launch_bounds__(1024) l2_sum_kernel(const float* __restrict__ x, int64_t n,
                                                       float coef, float* out) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i] * x[i];
@@ -154,7 +162,8 @@ __global__ void __launch_bounds__(1024) l2_sum_kernel(const float* __restrict__ 
   if (threadIdx.x == 0) *out = *out + coef * s;
 }
 
-__global__ void counter_add_kernel(int64_t* c, int64_t inc) { *c = *c + inc; }
+__global__ void counter_add_kernel(int64_t* c, int64_t inc) {
+  pdl_prologue(); *c = *c + inc; }
 
 static unsigned flat_grid(int64_t n) {
   int64_t blocks = (n + 255) / 256;
@@ -175,8 +184,7 @@ int b200rl_adam_tf(float* p, const float* g, float* m, float* v, int64_t n, floa
                    const float* grad_scale_dev, void* stream) {
   B200RL_CHECK_ARG(p && g && m && v && step_dev && n >= 0, "adam_tf: bad argument");
   if (n == 0) return B200RL_OK;
-  adam_tf_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, b1, b2, eps,
-                                                                 step_dev, grad_scale_dev);
+  B200RL_LAUNCH(adam_tf_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, p, g, m, v, n, lr, b1, b2, eps, step_dev, grad_scale_dev);
   B200RL_CHECK_LAUNCH("adam_tf");
   return B200RL_OK;
 }
@@ -187,8 +195,7 @@ int b200rl_rmsprop_tf(float* p, const float* g, float* ms, float* mg, float* mom
   B200RL_CHECK_ARG(p && g && ms && mom && n >= 0, "rmsprop_tf: bad argument");
   B200RL_CHECK_ARG(!centered || mg, "rmsprop_tf: centered needs mg");
   if (n == 0) return B200RL_OK;
-  rmsprop_tf_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(
-      p, g, ms, mg, mom, n, lr, decay, momentum, eps, centered, grad_scale_dev);
+  B200RL_LAUNCH(rmsprop_tf_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, p, g, ms, mg, mom, n, lr, decay, momentum, eps, centered, grad_scale_dev);
   B200RL_CHECK_LAUNCH("rmsprop_tf");
   return B200RL_OK;
 }
@@ -199,8 +206,7 @@ int b200rl_soft_update(float* target, const float* source, int64_t n, float tau,
   B200RL_CHECK_ARG(tau >= 0.f && tau <= 1.f, "Input `tau` should be in [0, 1].");
   B200RL_CHECK_ARG(period <= 1 || counter_dev, "soft_update: period>1 needs a counter");
   if (n == 0 || tau == 0.f) return B200RL_OK;  // utils/common.py:301-302 no-op
-  soft_update_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(target, source, n, tau,
-                                                                     period, counter_dev);
+  B200RL_LAUNCH(soft_update_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, target, source, n, tau, period, counter_dev);
   B200RL_CHECK_LAUNCH("soft_update");
   return B200RL_OK;
 }
@@ -209,8 +215,7 @@ int b200rl_clip_by_norm_segments(float* g, const int64_t* offsets_dev, int64_t n
                                  float max_norm, void* stream) {
   B200RL_CHECK_ARG(g && offsets_dev && nseg >= 0, "clip_by_norm_segments: bad argument");
   if (nseg == 0) return B200RL_OK;
-  clip_by_norm_segments_kernel<<<(unsigned)nseg, 1024, 0, (cudaStream_t)stream>>>(g, offsets_dev,
-                                                                                  max_norm);
+  B200RL_LAUNCH(clip_by_norm_segments_kernel, (unsigned)nseg, 1024, 0, (cudaStream_t)stream, g, offsets_dev, max_norm);
   B200RL_CHECK_LAUNCH("clip_by_norm_segments");
   return B200RL_OK;
 }
@@ -221,10 +226,9 @@ int b200rl_global_norm_scale(const float* g, int64_t n, float clip, float* scale
   B200RL_CHECK_ARG(workspace && ws_bytes >= (int64_t)(kNormBlocks * sizeof(float)),
                    "global_norm_scale: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
-  sumsq_partial_kernel<<<kNormBlocks, 256, 0, st>>>(g, n, (float*)workspace);
+  B200RL_LAUNCH(sumsq_partial_kernel, kNormBlocks, 256, 0, st, g, n, (float*)workspace);
   B200RL_CHECK_LAUNCH("sumsq_partial");
-  global_norm_final_kernel<<<1, 512, 0, st>>>((const float*)workspace, kNormBlocks, clip,
-                                              scale_dev, norm_dev);
+  B200RL_LAUNCH(global_norm_final_kernel, 1, 512, 0, st, (const float*)workspace, kNormBlocks, clip, scale_dev, norm_dev);
   B200RL_CHECK_LAUNCH("global_norm_final");
   return B200RL_OK;
 }
@@ -232,21 +236,21 @@ int b200rl_global_norm_scale(const float* g, int64_t n, float clip, float* scale
 int b200rl_add_scaled(float* dst, const float* src, int64_t n, float alpha, void* stream) {
   B200RL_CHECK_ARG(dst && src && n >= 0, "add_scaled: bad argument");
   if (n == 0) return B200RL_OK;
-  add_scaled_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(dst, src, n, alpha);
+  B200RL_LAUNCH(add_scaled_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, dst, src, n, alpha);
   B200RL_CHECK_LAUNCH("add_scaled");
   return B200RL_OK;
 }
 
 int b200rl_l2_sum(const float* x, int64_t n, float coef, float* out_accum, void* stream) {
   B200RL_CHECK_ARG(x && out_accum && n >= 0, "l2_sum: bad argument");
-  l2_sum_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, coef, out_accum);
+  B200RL_LAUNCH(l2_sum_kernel, 1, 1024, 0, (cudaStream_t)stream, x, n, coef, out_accum);
   B200RL_CHECK_LAUNCH("l2_sum");
   return B200RL_OK;
 }
 
 int b200rl_counter_add(int64_t* counter_dev, int64_t inc, void* stream) {
   B200RL_CHECK_ARG(counter_dev, "counter_add: NULL");
-  counter_add_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(counter_dev, inc);
+  B200RL_LAUNCH(counter_add_kernel, 1, 1, 0, (cudaStream_t)stream, counter_dev, inc);
   B200RL_CHECK_LAUNCH("counter_add");
   return B200RL_OK;
 }

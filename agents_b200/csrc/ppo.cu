@@ -31,9 +31,23 @@ struct PpoArgs {
   float* dloc; float* dscale; int64_t ld_g;                  // gradients, same column layout
   float* dv;                                                 // [N]
   float* partial;                                            // [kRedBlocks, 4]
+  // KL penalty (ppo_agent.py:1514-1630): behaviour policy Normal(old_loc, old_scale); the
+  // scalar d(kl_penalty)/d(mean_kl) sits in kl_terms[2] (b200rl_ppo_kl_terms)
+  const float* old_loc; const float* old_scale; int64_t ld_old;
+  const float* kl_terms; float kl_grad_scale;
 };
 
+// KL(Normal(mu_a, s_a) || Normal(mu_b, s_b)) per dimension, TFP's closed form
+// (tfp.distributions.normal._kl_normal_normal): 0.5*((mu_a - mu_b)/s_b)^2 + 0.5*expm1(2d) - d,
+// d = log s_a - log s_b.
+__device__ __forceinline__ float kl_normal(float mu_a, float s_a, float mu_b, float s_b) {
+  const float d = logf(s_a) - logf(s_b);
+  const float z = mu_a / s_b - mu_b / s_b;
+  return 0.5f * z * z + 0.5f * expm1f(2.f * d) - d;
+}
+
 __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoArgs a) {
+  pdl_prologue();
   __shared__ float red[32];
   float s_pg = 0.f, s_ve = 0.f, s_ent = 0.f, s_clip = 0.f;
   const float denom = (float)a.T * a.global_batch;  // mean over T, then sum over B / global B
@@ -89,12 +103,22 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoArgs a) {
     // gradients of total = pg + vf_coef*ve + ent_coef*ent_loss
     const float g_logp = -dobj_dratio * ratio * dlp * w / denom;   // dL_pg / dlogp
     const float g_ent = -a.ent_coef * w / denom;                   // dL_ent / d(entropy)
+    // d(kl_penalty)/d(kl_n) = (2 c max(mean_kl - cutoff, 0) + beta) * w_n / N_global
+    const float g_kl = a.kl_terms ? a.kl_terms[2] * a.kl_grad_scale * w : 0.f;
     for (int64_t k = 0; k < a.A; ++k) {
       const float mu = a.loc[n * a.ld_ls + k], sg = a.scale[n * a.ld_ls + k];
       const float d = a.action[n * a.A + k] - mu;
       const float inv = 1.f / sg;
-      a.dloc[n * a.ld_g + k] = g_logp * d * inv * inv;
-      a.dscale[n * a.ld_g + k] = g_logp * (d * d * inv * inv * inv - inv) + g_ent * inv;
+      float gl = g_logp * d * inv * inv;
+      float gs = g_logp * (d * d * inv * inv * inv - inv) + g_ent * inv;
+      if (a.kl_terms) {   // KL(old || new) w.r.t. the new (mu, sigma)
+        const float mo = a.old_loc[n * a.ld_old + k], so = a.old_scale[n * a.ld_old + k];
+        const float dm = mo - mu;
+        gl += g_kl * (-dm * inv * inv);
+        gs += g_kl * (inv - (dm * dm + so * so) * inv * inv * inv);
+      }
+      a.dloc[n * a.ld_g + k] = gl;
+      a.dscale[n * a.ld_g + k] = gs;
     }
     a.dv[n] = a.vf_coef * derr_dv * w / denom;
   }
@@ -108,13 +132,15 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(const PpoArgs a) {
   }
 }
 
-// losses[0..4] = {policy_gradient, value_estimation, entropy_regularization, clip_fraction,
-//                 total (without l2/kl)}
+// losses[0..5] = {policy_gradient, value_estimation, entropy_regularization, clip_fraction,
+//                 total (without l2), kl_penalty}
 __global__ void __launch_bounds__(512) ppo_loss_final_kernel(const float* __restrict__ partial,
                                                              int nblocks, float denom, float n,
                                                              float vf_coef, float ent_coef,
+                                                             const float* __restrict__ kl_terms,
                                                              float* __restrict__ losses,
                                                              int32_t* nan_flag) {
+  pdl_prologue();
   __shared__ float red[32];
   float v[4];
 #pragma unroll
@@ -129,7 +155,9 @@ __global__ void __launch_bounds__(512) ppo_loss_final_kernel(const float* __rest
     losses[1] = ve;
     losses[2] = en;
     losses[3] = v[3] / n;
-    losses[4] = pg + ve + en;
+    const float kl = kl_terms ? kl_terms[0] + kl_terms[1] : 0.f;   // kl_penalty_loss (:1628-1630)
+    losses[5] = kl;
+    losses[4] = pg + ve + en + kl;
     if (nan_flag && !isfinite(losses[4])) *nan_flag = 1;
   }
 }
@@ -137,6 +165,7 @@ __global__ void __launch_bounds__(512) ppo_loss_final_kernel(const float* __rest
 __global__ void normal_logp_kernel(const float* __restrict__ loc, const float* __restrict__ scale,
                                    int64_t ld, const float* __restrict__ action, int64_t N,
                                    int64_t A, float* __restrict__ out) {
+  pdl_prologue();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float logp = 0.f;
@@ -155,6 +184,7 @@ __global__ void normal_sample_kernel(const float* __restrict__ loc,
                                      int64_t A, const float* __restrict__ amin,
                                      const float* __restrict__ amax, uint64_t seed,
                                      uint64_t* rng_call, float* __restrict__ out) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < N * A) {
     const int64_t n = i / A, k = i - n * A;
@@ -185,6 +215,7 @@ __global__ void normal_proj_fwd_kernel(const float* __restrict__ m_raw,
                                        const float* __restrict__ amin,
                                        const float* __restrict__ amax, int64_t N, int64_t A,
                                        float* __restrict__ loc, float* __restrict__ scale) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * A) return;
   const int64_t k = i % A;
@@ -202,6 +233,7 @@ __global__ void normal_proj_bwd_kernel(const float* __restrict__ m_raw,
                                        const float* __restrict__ dloc,
                                        const float* __restrict__ dscale, int64_t N, int64_t A,
                                        float* __restrict__ dm_raw, float* __restrict__ ds_part) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * A) return;
   const int64_t k = i % A;
@@ -216,6 +248,7 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
                                                           const float* __restrict__ center,
                                                           int squared, int64_t rows, int64_t cols,
                                                           float* __restrict__ part) {
+  pdl_prologue();
   // grid = (cols, nblk): block (c, j) sums rows j, j+nblk, ... of column c
   __shared__ float red[32];
   const int64_t c = blockIdx.x;
@@ -231,6 +264,7 @@ __global__ void __launch_bounds__(256) colsum_rows_kernel(const float* __restric
 }
 __global__ void colsum_rows_final_kernel(const float* __restrict__ part, int nblk, int64_t cols,
                                          float scale, float* __restrict__ out) {
+  pdl_prologue();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -244,6 +278,7 @@ __global__ void normalize_kernel(const float* __restrict__ x, float* __restrict_
                                  int64_t rows, int64_t cols, const float* __restrict__ mean,
                                  const float* __restrict__ m2, const float* __restrict__ count,
                                  float eps, float clip) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * cols) return;
   const int64_t c = i % cols;
@@ -260,6 +295,7 @@ __global__ void normalizer_update_kernel(float* __restrict__ count, float* __res
                                          float* __restrict__ m2, float* __restrict__ carry,
                                          const float* __restrict__ avg_a,
                                          const float* __restrict__ m2_a, float n_a, int64_t cols) {
+  pdl_prologue();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const float n_b = count[c], avg_b = avg[c], m2_b = m2[c], m2_b_c = carry[c];
@@ -280,6 +316,7 @@ __global__ void normalizer_update_kernel(float* __restrict__ count, float* __res
 __global__ void ppo_discounts_kernel(const float* __restrict__ discount,
                                      const int32_t* __restrict__ next_step_type, float gamma,
                                      int64_t n, float* __restrict__ out) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float mask = next_step_type[i] == kStepLastP ? 0.f : 1.f;
@@ -291,10 +328,79 @@ __global__ void ppo_weights_kernel(const int32_t* __restrict__ step_type,
                                    const float* __restrict__ ret, const float* __restrict__ adv,
                                    const float* __restrict__ weights, int64_t n,
                                    float* __restrict__ out) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const bool valid = step_type[i] != kStepLastP && !(ret[i] == 0.f && adv[i] == 0.f);
   out[i] = valid ? (weights ? weights[i] : 1.f) : 0.f;
+}
+
+
+// sum_n w_n * KL(old_n || new_n) in two fixed-order stages (kl_penalty_loss :1613-1617); the
+// weighted per-element values are optionally kept (update_adaptive_kl_beta, debug).
+__global__ void __launch_bounds__(256) ppo_kl_partial_kernel(
+    const float* __restrict__ loc, const float* __restrict__ scale, int64_t ld,
+    const float* __restrict__ old_loc, const float* __restrict__ old_scale, int64_t ld_old,
+    const float* __restrict__ w, int64_t N, int64_t A, float* __restrict__ out_kl,
+    float* __restrict__ partial) {
+  pdl_prologue();
+  __shared__ float red[32];
+  float s = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += stride) {
+    float kl = 0.f;
+    for (int64_t k = 0; k < A; ++k)
+      kl += kl_normal(old_loc[n * ld_old + k], old_scale[n * ld_old + k], loc[n * ld + k],
+                      scale[n * ld + k]);
+    kl *= w ? w[n] : 1.f;
+    if (out_kl) out_kl[n] = kl;
+    s += kl;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) partial[blockIdx.x] = s;
+}
+__global__ void __launch_bounds__(512) ppo_kl_final_kernel(const float* __restrict__ partial,
+                                                           int nblocks, float scale,
+                                                           float* __restrict__ out) {
+  pdl_prologue();
+  __shared__ float red[32];
+  float s = (threadIdx.x < nblocks) ? partial[threadIdx.x] : 0.f;
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) *out = s * scale;
+}
+
+// terms[3] = {kl_cutoff_loss (:1514-1539), adaptive_kl_loss (:1541-1558),
+//             d(kl_cutoff_loss + adaptive_kl_loss)/d(mean_kl)}
+__global__ void ppo_kl_terms_kernel(const float* __restrict__ mean_kl,
+                                    const float* __restrict__ beta, float cutoff,
+                                    float cutoff_coef, int use_cutoff,
+                                    float* __restrict__ terms) {
+  pdl_prologue();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float m = *mean_kl;
+  float cut = 0.f, dcut = 0.f;
+  if (use_cutoff) {
+    const float over = fmaxf(m - cutoff, 0.f);
+    cut = cutoff_coef * over * over;
+    dcut = 2.f * cutoff_coef * over;
+  }
+  const float b = beta ? *beta : 0.f;
+  terms[0] = cut;
+  terms[1] = b * m;
+  terms[2] = dcut + b;
+}
+
+// update_adaptive_kl_beta (:1632-1675): x1.5 above target*(1+tol), /1.5 below target*(1-tol),
+// clipped to [10e-16, 10e16].
+__global__ void ppo_kl_beta_update_kernel(const float* __restrict__ mean_kl,
+                                          float* __restrict__ beta, float target, float tol) {
+  pdl_prologue();
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float m = *mean_kl;
+  float f = 1.f;
+  if (m < target * (1.f - tol)) f = 1.f / 1.5f;
+  else if (m > target * (1.f + tol)) f = 1.5f;
+  *beta = fminf(fmaxf(*beta * f, 10e-16f), 10e16f);
 }
 
 }  // namespace b200rl
@@ -310,8 +416,8 @@ int b200rl_ppo_loss(const float* loc, const float* scale, int64_t ld_ls, const f
                     const float* v_old, const float* w, int64_t N, int64_t A, int64_t T,
                     float global_batch, float clip_eps, float value_clip, float vf_coef,
                     float ent_coef, float logp_clip, float* losses, float* dloc, float* dscale,
-                    int64_t ld_g, float* dv, int32_t* nan_flag, void* workspace,
-                    int64_t ws_bytes, void* stream) {
+                    int64_t ld_g, float* dv, int32_t* nan_flag, const b200rl_ppo_kl_t* kl,
+                    void* workspace, int64_t ws_bytes, void* stream) {
   B200RL_CHECK_ARG(loc && scale && action && old_logp && adv && ret && v && w && losses && dloc &&
                        dscale && dv,
                    "ppo_loss: NULL argument");
@@ -323,14 +429,54 @@ int b200rl_ppo_loss(const float* loc, const float* scale, int64_t ld_ls, const f
   cudaStream_t st = (cudaStream_t)stream;
   PpoArgs a{loc, scale, ld_ls, action, old_logp, adv, ret, v, v_old, w, N, A, T, global_batch,
             clip_eps, value_clip, vf_coef, ent_coef, logp_clip, dloc, dscale, ld_g, dv,
-            (float*)workspace};
+            (float*)workspace, nullptr, nullptr, 0, nullptr, 0.f};
+  if (kl != nullptr) {
+    B200RL_CHECK_ARG(kl->old_loc && kl->old_scale && kl->terms && kl->ld_old >= A,
+                     "ppo_loss: incomplete KL-penalty arguments");
+    a.old_loc = kl->old_loc; a.old_scale = kl->old_scale; a.ld_old = kl->ld_old;
+    a.kl_terms = kl->terms; a.kl_grad_scale = kl->grad_scale;
+  }
   int nb = (int)((N + 255) / 256);
   if (nb > kRedBlocks) nb = kRedBlocks;
-  ppo_loss_kernel<<<nb, 256, 0, st>>>(a);
+  B200RL_LAUNCH(ppo_loss_kernel, nb, 256, 0, st, a);
   B200RL_CHECK_LAUNCH("ppo_loss");
-  ppo_loss_final_kernel<<<1, 512, 0, st>>>((const float*)workspace, nb, (float)T * global_batch,
-                                           (float)N, vf_coef, ent_coef, losses, nan_flag);
+  B200RL_LAUNCH(ppo_loss_final_kernel, 1, 512, 0, st, (const float*)workspace, nb, (float)T * global_batch, (float)N, vf_coef, ent_coef, a.kl_terms, losses, nan_flag);
   B200RL_CHECK_LAUNCH("ppo_loss_final");
+  return B200RL_OK;
+}
+
+int b200rl_ppo_kl(const float* loc, const float* scale, int64_t ld, const float* old_loc,
+                  const float* old_scale, int64_t ld_old, const float* w, int64_t N, int64_t A,
+                  float out_scale, float* out_kl, float* out_sum, void* workspace,
+                  int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(loc && scale && old_loc && old_scale && out_sum, "ppo_kl: NULL argument");
+  B200RL_CHECK_ARG(N >= 1 && A >= 1 && ld >= A && ld_old >= A, "ppo_kl: bad sizes");
+  B200RL_CHECK_ARG(workspace && ws_bytes >= (int64_t)(kRedBlocks * sizeof(float)),
+                   "ppo_kl: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  int nb = (int)((N + 255) / 256);
+  if (nb > kRedBlocks) nb = kRedBlocks;
+  B200RL_LAUNCH(ppo_kl_partial_kernel, nb, 256, 0, st, loc, scale, ld, old_loc, old_scale, ld_old, w, N, A, out_kl, (float*)workspace);
+  B200RL_CHECK_LAUNCH("ppo_kl_partial");
+  B200RL_LAUNCH(ppo_kl_final_kernel, 1, 512, 0, st, (const float*)workspace, nb, out_scale, out_sum);
+  B200RL_CHECK_LAUNCH("ppo_kl_final");
+  return B200RL_OK;
+}
+
+int b200rl_ppo_kl_terms(const float* mean_kl_dev, const float* beta_dev, float kl_cutoff_factor,
+                        float adaptive_kl_target, float kl_cutoff_coef, float* terms_dev,
+                        void* stream) {
+  B200RL_CHECK_ARG(mean_kl_dev && terms_dev, "ppo_kl_terms: NULL argument");
+  B200RL_LAUNCH(ppo_kl_terms_kernel, 1, 32, 0, (cudaStream_t)stream, mean_kl_dev, beta_dev, kl_cutoff_factor * adaptive_kl_target, kl_cutoff_coef, kl_cutoff_factor > 0.f ? 1 : 0, terms_dev);
+  B200RL_CHECK_LAUNCH("ppo_kl_terms");
+  return B200RL_OK;
+}
+
+int b200rl_ppo_kl_beta_update(const float* mean_kl_dev, float* beta_dev, float adaptive_kl_target,
+                              float adaptive_kl_tolerance, void* stream) {
+  B200RL_CHECK_ARG(mean_kl_dev && beta_dev, "ppo_kl_beta_update: NULL argument");
+  B200RL_LAUNCH(ppo_kl_beta_update_kernel, 1, 32, 0, (cudaStream_t)stream, mean_kl_dev, beta_dev, adaptive_kl_target, adaptive_kl_tolerance);
+  B200RL_CHECK_LAUNCH("ppo_kl_beta_update");
   return B200RL_OK;
 }
 
@@ -339,8 +485,7 @@ int b200rl_normal_logp(const float* loc, const float* scale, int64_t ld, const f
   B200RL_CHECK_ARG(loc && scale && action && out && N >= 0 && A >= 1 && ld >= A,
                    "normal_logp: bad argument");
   if (N == 0) return B200RL_OK;
-  normal_logp_kernel<<<blocks_for(N), 256, 0, (cudaStream_t)stream>>>(loc, scale, ld, action, N, A,
-                                                                      out);
+  B200RL_LAUNCH(normal_logp_kernel, blocks_for(N), 256, 0, (cudaStream_t)stream, loc, scale, ld, action, N, A, out);
   B200RL_CHECK_LAUNCH("normal_logp");
   return B200RL_OK;
 }
@@ -351,8 +496,7 @@ int b200rl_normal_sample(const float* loc, const float* scale, int64_t ld, int64
   B200RL_CHECK_ARG(loc && scale && out && rng_call_dev && N >= 1 && A >= 1 && ld >= A,
                    "normal_sample: bad argument");
   B200RL_CHECK_ARG((amin == nullptr) == (amax == nullptr), "normal_sample: amin/amax mismatch");
-  normal_sample_kernel<<<blocks_for(N * A), 256, 0, (cudaStream_t)stream>>>(
-      loc, scale, ld, N, A, amin, amax, seed, rng_call_dev, out);
+  B200RL_LAUNCH(normal_sample_kernel, blocks_for(N * A), 256, 0, (cudaStream_t)stream, loc, scale, ld, N, A, amin, amax, seed, rng_call_dev, out);
   B200RL_CHECK_LAUNCH("normal_sample");
   return B200RL_OK;
 }
@@ -362,8 +506,7 @@ int b200rl_normal_proj_fwd(const float* m_raw, const float* s_raw, const float* 
                            void* stream) {
   B200RL_CHECK_ARG(m_raw && s_raw && amin && amax && loc && scale && N >= 1 && A >= 1,
                    "normal_proj_fwd: bad argument");
-  normal_proj_fwd_kernel<<<blocks_for(N * A), 256, 0, (cudaStream_t)stream>>>(m_raw, s_raw, amin,
-                                                                              amax, N, A, loc, scale);
+  B200RL_LAUNCH(normal_proj_fwd_kernel, blocks_for(N * A), 256, 0, (cudaStream_t)stream, m_raw, s_raw, amin, amax, N, A, loc, scale);
   B200RL_CHECK_LAUNCH("normal_proj_fwd");
   return B200RL_OK;
 }
@@ -374,8 +517,7 @@ int b200rl_normal_proj_bwd(const float* m_raw, const float* s_raw, const float* 
   B200RL_CHECK_ARG(m_raw && s_raw && amin && amax && dloc && dscale && dm_raw && ds_part &&
                        N >= 1 && A >= 1,
                    "normal_proj_bwd: bad argument");
-  normal_proj_bwd_kernel<<<blocks_for(N * A), 256, 0, (cudaStream_t)stream>>>(
-      m_raw, s_raw, amin, amax, dloc, dscale, N, A, dm_raw, ds_part);
+  B200RL_LAUNCH(normal_proj_bwd_kernel, blocks_for(N * A), 256, 0, (cudaStream_t)stream, m_raw, s_raw, amin, amax, dloc, dscale, N, A, dm_raw, ds_part);
   B200RL_CHECK_LAUNCH("normal_proj_bwd");
   return B200RL_OK;
 }
@@ -392,10 +534,9 @@ int b200rl_colsum(const float* x, const float* center, int squared, int64_t rows
                    "colsum: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)cols, (unsigned)nblk);
-  colsum_rows_kernel<<<grid, 256, 0, st>>>(x, center, squared, rows, cols, (float*)workspace);
+  B200RL_LAUNCH(colsum_rows_kernel, grid, 256, 0, st, x, center, squared, rows, cols, (float*)workspace);
   B200RL_CHECK_LAUNCH("colsum_rows");
-  colsum_rows_final_kernel<<<blocks_for(cols), 256, 0, st>>>((const float*)workspace, nblk, cols,
-                                                             scale, out);
+  B200RL_LAUNCH(colsum_rows_final_kernel, blocks_for(cols), 256, 0, st, (const float*)workspace, nblk, cols, scale, out);
   B200RL_CHECK_LAUNCH("colsum_rows_final");
   return B200RL_OK;
 }
@@ -403,8 +544,7 @@ int b200rl_colsum(const float* x, const float* center, int squared, int64_t rows
 int b200rl_normalize(const float* x, float* out, int64_t rows, int64_t cols, const float* mean,
                      const float* m2, const float* count, float eps, float clip, void* stream) {
   B200RL_CHECK_ARG(x && out && m2 && rows >= 1 && cols >= 1, "normalize: bad argument");
-  normalize_kernel<<<blocks_for(rows * cols), 256, 0, (cudaStream_t)stream>>>(
-      x, out, rows, cols, mean, m2, count, eps, clip);
+  B200RL_LAUNCH(normalize_kernel, blocks_for(rows * cols), 256, 0, (cudaStream_t)stream, x, out, rows, cols, mean, m2, count, eps, clip);
   B200RL_CHECK_LAUNCH("normalize");
   return B200RL_OK;
 }
@@ -414,8 +554,7 @@ int b200rl_normalizer_update(float* count, float* avg, float* m2, float* carry,
                              void* stream) {
   B200RL_CHECK_ARG(count && avg && m2 && carry && avg_a && m2_a && cols >= 1,
                    "normalizer_update: bad argument");
-  normalizer_update_kernel<<<blocks_for(cols), 256, 0, (cudaStream_t)stream>>>(
-      count, avg, m2, carry, avg_a, m2_a, n_a, cols);
+  B200RL_LAUNCH(normalizer_update_kernel, blocks_for(cols), 256, 0, (cudaStream_t)stream, count, avg, m2, carry, avg_a, m2_a, n_a, cols);
   B200RL_CHECK_LAUNCH("normalizer_update");
   return B200RL_OK;
 }
@@ -423,8 +562,7 @@ int b200rl_normalizer_update(float* count, float* avg, float* m2, float* carry,
 int b200rl_ppo_discounts(const float* discount, const int32_t* next_step_type, float gamma,
                          int64_t n, float* out, void* stream) {
   B200RL_CHECK_ARG(discount && next_step_type && out && n >= 1, "ppo_discounts: bad argument");
-  ppo_discounts_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(discount, next_step_type,
-                                                                        gamma, n, out);
+  B200RL_LAUNCH(ppo_discounts_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, discount, next_step_type, gamma, n, out);
   B200RL_CHECK_LAUNCH("ppo_discounts");
   return B200RL_OK;
 }
@@ -432,8 +570,7 @@ int b200rl_ppo_discounts(const float* discount, const int32_t* next_step_type, f
 int b200rl_ppo_weights(const int32_t* step_type, const float* ret, const float* adv,
                        const float* weights, int64_t n, float* out, void* stream) {
   B200RL_CHECK_ARG(step_type && ret && adv && out && n >= 1, "ppo_weights: bad argument");
-  ppo_weights_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(step_type, ret, adv, weights,
-                                                                      n, out);
+  B200RL_LAUNCH(ppo_weights_kernel, blocks_for(n), 256, 0, (cudaStream_t)stream, step_type, ret, adv, weights, n, out);
   B200RL_CHECK_LAUNCH("ppo_weights");
   return B200RL_OK;
 }

@@ -206,6 +206,7 @@ __device__ __forceinline__ void finish(const Plan& p, int64_t last, bool ok) {
 // small leaves and the id / row / probability outputs.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) row_copy_big(const __grid_constant__ Plan p) {
+  pdl_prologue();
   const int64_t blk = blockIdx.x;
   const int64_t s = blk / p.pieces_per_row;
   int piece = (int)(blk - s * p.pieces_per_row);
@@ -241,6 +242,7 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 template <int MODE>
 __global__ void __launch_bounds__(32) row_copy_tma(const __grid_constant__ Plan p) {
+  pdl_prologue();
   extern __shared__ __align__(128) unsigned char stage[];
   __shared__ __align__(8) unsigned long long bar;
   const int64_t blk = blockIdx.x;
@@ -298,6 +300,7 @@ __global__ void __launch_bounds__(32) row_copy_tma(const __grid_constant__ Plan 
 // All-small rows (MuJoCo-shape: 108-160 B): one warp per row, 8 rows per CTA.
 template <int MODE>
 __global__ void __launch_bounds__(kThreads) row_copy_small(const __grid_constant__ Plan p) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t s = (int64_t)blockIdx.x * (kThreads / 32) + warp;
   const int64_t last = p.last_id ? *p.last_id : 0;
@@ -315,6 +318,7 @@ __global__ void __launch_bounds__(kThreads) row_copy_small(const __grid_constant
 }
 
 __global__ void draw_kernel(const __grid_constant__ Plan p) {
+  pdl_prologue();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t last = *p.last_id;
   int64_t lo, hi;
@@ -337,7 +341,8 @@ __global__ void draw_kernel(const __grid_constant__ Plan p) {
   }
 }
 
-__global__ void clear_kernel(int64_t* last_id) { *last_id = -1; }
+__global__ void clear_kernel(int64_t* last_id) {
+  pdl_prologue(); *last_id = -1; }
 
 // 0 = LDG/STG kernel (row_copy_big), 1 = TMA bulk-copy kernel (row_copy_tma).
 // B200RL_COPY_VARIANT overrides the default (used by profiles/gather_sweep.py for A/B runs).
@@ -414,14 +419,14 @@ static int launch_plan(Plan& p, cudaStream_t st, const char* name) {
       if (p.big[i].piece_bytes > max_piece) max_piece = p.big[i].piece_bytes;
     }
     if (tma_ok) {
-      row_copy_tma<MODE><<<(unsigned)grid, 32, max_piece, st>>>(p);
+      B200RL_LAUNCH(row_copy_tma<MODE>, (unsigned)grid, 32, max_piece, st, p);
     } else {
-      row_copy_big<MODE><<<(unsigned)grid, kThreads, 0, st>>>(p);
+      B200RL_LAUNCH(row_copy_big<MODE>, (unsigned)grid, kThreads, 0, st, p);
     }
   } else {
     int64_t grid = (p.n_rows + p.rows_per_cta - 1) / p.rows_per_cta;
     B200RL_CHECK_ARG(grid < (1ll << 31), "%s: grid too large", name);
-    row_copy_small<MODE><<<(unsigned)grid, kThreads, 0, st>>>(p);
+    B200RL_LAUNCH(row_copy_small<MODE>, (unsigned)grid, kThreads, 0, st, p);
   }
   B200RL_CHECK_LAUNCH(name);
   return B200RL_OK;
@@ -518,7 +523,7 @@ int b200rl_rb_gather_all(const b200rl_ring_t* ring, int64_t n_valid, void* const
 int b200rl_rb_clear(const b200rl_ring_t* ring, int clear_all, void* stream) {
   B200RL_CHECK_ARG(ring != nullptr && ring->last_id != nullptr, "rb_clear: ring is NULL");
   cudaStream_t st = (cudaStream_t)stream;
-  clear_kernel<<<1, 1, 0, st>>>(ring->last_id);
+  B200RL_LAUNCH(clear_kernel, 1, 1, 0, st, ring->last_id);
   B200RL_CHECK_LAUNCH("rb_clear");
   if (clear_all) {
     const int64_t cap = ring->batch_size * ring->max_length;
@@ -552,7 +557,7 @@ int b200rl_rb_draw(const b200rl_ring_t* ring, int64_t B, int64_t T, uint64_t see
   p.out_draw_ids = out_ids;
   p.out_draw_offs = out_offs;
   unsigned grid = (unsigned)((B + 255) / 256);
-  draw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  B200RL_LAUNCH(draw_kernel, grid, 256, 0, (cudaStream_t)stream, p);
   B200RL_CHECK_LAUNCH("rb_draw");
   return B200RL_OK;
 }

@@ -27,6 +27,7 @@ __global__ void sac_sample_kernel(const float* __restrict__ head, int64_t N, int
                                   uint64_t* rng_call, float* __restrict__ action, int64_t ld_a,
                                   float* __restrict__ logp, float* __restrict__ u_out,
                                   float* __restrict__ eps_out) {
+  pdl_prologue();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n < N) {
     float lp = 0.f;
@@ -73,6 +74,7 @@ __global__ void sac_sample_bwd_kernel(const float* __restrict__ head,
                                       const float* __restrict__ da1, const float* __restrict__ da2,
                                       int64_t ld_da, const float* __restrict__ dlogp, int64_t N,
                                       int64_t A, float* __restrict__ dhead) {
+  pdl_prologue();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * A) return;
   const int64_t n = i / A, k = i - n * A;
@@ -97,6 +99,7 @@ __global__ void __launch_bounds__(256) sac_critic_loss_kernel(
     float gamma, float reward_scale, float loss_weight, float global_batch,
     float* __restrict__ loss, float* __restrict__ dq1, float* __restrict__ dq2,
     float* __restrict__ td_targets, int32_t* nan_flag) {
+  pdl_prologue();
   __shared__ float red[32];
   const float alpha = expf(log_alpha[0]);
   float s = 0.f;
@@ -125,6 +128,7 @@ __global__ void __launch_bounds__(256) sac_actor_loss_kernel(
     const float* __restrict__ weights, const float* __restrict__ log_alpha, int64_t B,
     float loss_weight, float global_batch, float* __restrict__ loss, float* __restrict__ dlogp,
     float* __restrict__ dq1, float* __restrict__ dq2, int32_t* nan_flag) {
+  pdl_prologue();
   __shared__ float red[32];
   const float alpha = expf(log_alpha[0]);
   float s = 0.f;
@@ -153,6 +157,7 @@ __global__ void __launch_bounds__(256) sac_alpha_loss_kernel(
     const float* __restrict__ log_alpha, int64_t B, float target_entropy, int use_log_alpha,
     float loss_weight, float global_batch, float* __restrict__ loss,
     float* __restrict__ dlog_alpha, int32_t* nan_flag) {
+  pdl_prologue();
   __shared__ float red[32];
   float s = 0.f;
   for (int64_t b = threadIdx.x; b < B; b += blockDim.x) {
@@ -175,6 +180,7 @@ __global__ void __launch_bounds__(256) sac_alpha_loss_kernel(
 __global__ void concat2_kernel(const float* __restrict__ a, int64_t lda, int64_t da,
                                const float* __restrict__ b, int64_t ldb, int64_t db, int64_t N,
                                float* __restrict__ out) {
+  pdl_prologue();
   const int64_t w = da + db;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * w) return;
@@ -197,8 +203,7 @@ int b200rl_sac_sample(const float* head, int64_t N, int64_t A, const float* amin
   B200RL_CHECK_ARG(head && amin && amax && action && logp && N >= 1 && A >= 1 && ld_action >= A,
                    "sac_sample: bad argument");
   B200RL_CHECK_ARG(eps_in || rng_call_dev, "sac_sample: need eps or rng_call_dev");
-  sac_sample_kernel<<<sac_blocks(N), 256, 0, (cudaStream_t)stream>>>(
-      head, N, A, amin, amax, eps_in, seed, rng_call_dev, action, ld_action, logp, u_out, eps_out);
+  B200RL_LAUNCH(sac_sample_kernel, sac_blocks(N), 256, 0, (cudaStream_t)stream, head, N, A, amin, amax, eps_in, seed, rng_call_dev, action, ld_action, logp, u_out, eps_out);
   B200RL_CHECK_LAUNCH("sac_sample");
   return B200RL_OK;
 }
@@ -210,8 +215,7 @@ int b200rl_sac_sample_bwd(const float* head, const float* u_saved, const float* 
   B200RL_CHECK_ARG(head && u_saved && eps_saved && amin && amax && dlogp && dhead && N >= 1 &&
                        A >= 1,
                    "sac_sample_bwd: bad argument");
-  sac_sample_bwd_kernel<<<sac_blocks(N * A), 256, 0, (cudaStream_t)stream>>>(
-      head, u_saved, eps_saved, amin, amax, da1, da2, ld_da, dlogp, N, A, dhead);
+  B200RL_LAUNCH(sac_sample_bwd_kernel, sac_blocks(N * A), 256, 0, (cudaStream_t)stream, head, u_saved, eps_saved, amin, amax, da1, da2, ld_da, dlogp, N, A, dhead);
   B200RL_CHECK_LAUNCH("sac_sample_bwd");
   return B200RL_OK;
 }
@@ -225,9 +229,7 @@ int b200rl_sac_critic_loss(const float* q1, const float* q2, const float* tq1, c
   B200RL_CHECK_ARG(q1 && q2 && tq1 && tq2 && next_logp && reward && discount && log_alpha_dev &&
                        loss && dq1 && dq2 && B >= 1 && global_batch > 0.f,
                    "sac_critic_loss: bad argument");
-  sac_critic_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
-      q1, q2, tq1, tq2, next_logp, reward, discount, weights, log_alpha_dev, B, gamma,
-      reward_scale, loss_weight, global_batch, loss, dq1, dq2, td_targets, nan_flag);
+  B200RL_LAUNCH(sac_critic_loss_kernel, 1, 256, 0, (cudaStream_t)stream, q1, q2, tq1, tq2, next_logp, reward, discount, weights, log_alpha_dev, B, gamma, reward_scale, loss_weight, global_batch, loss, dq1, dq2, td_targets, nan_flag);
   B200RL_CHECK_LAUNCH("sac_critic_loss");
   return B200RL_OK;
 }
@@ -239,9 +241,7 @@ int b200rl_sac_actor_loss(const float* q1, const float* q2, const float* logp,
   B200RL_CHECK_ARG(q1 && q2 && logp && log_alpha_dev && loss && dlogp && dq1 && dq2 && B >= 1 &&
                        global_batch > 0.f,
                    "sac_actor_loss: bad argument");
-  sac_actor_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
-      q1, q2, logp, weights, log_alpha_dev, B, loss_weight, global_batch, loss, dlogp, dq1, dq2,
-      nan_flag);
+  B200RL_LAUNCH(sac_actor_loss_kernel, 1, 256, 0, (cudaStream_t)stream, q1, q2, logp, weights, log_alpha_dev, B, loss_weight, global_batch, loss, dlogp, dq1, dq2, nan_flag);
   B200RL_CHECK_LAUNCH("sac_actor_loss");
   return B200RL_OK;
 }
@@ -252,9 +252,7 @@ int b200rl_sac_alpha_loss(const float* logp, const float* weights, const float* 
                           void* stream) {
   B200RL_CHECK_ARG(logp && log_alpha_dev && loss && dlog_alpha && B >= 1 && global_batch > 0.f,
                    "sac_alpha_loss: bad argument");
-  sac_alpha_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(
-      logp, weights, log_alpha_dev, B, target_entropy, use_log_alpha, loss_weight, global_batch,
-      loss, dlog_alpha, nan_flag);
+  B200RL_LAUNCH(sac_alpha_loss_kernel, 1, 256, 0, (cudaStream_t)stream, logp, weights, log_alpha_dev, B, target_entropy, use_log_alpha, loss_weight, global_batch, loss, dlog_alpha, nan_flag);
   B200RL_CHECK_LAUNCH("sac_alpha_loss");
   return B200RL_OK;
 }
@@ -263,8 +261,7 @@ int b200rl_concat2(const float* a, int64_t lda, int64_t da, const float* b, int6
                    int64_t db, int64_t N, float* out, void* stream) {
   B200RL_CHECK_ARG(a && b && out && N >= 1 && da >= 1 && db >= 1 && lda >= da && ldb >= db,
                    "concat2: bad argument");
-  concat2_kernel<<<sac_blocks(N * (da + db)), 256, 0, (cudaStream_t)stream>>>(a, lda, da, b, ldb,
-                                                                             db, N, out);
+  B200RL_LAUNCH(concat2_kernel, sac_blocks(N * (da + db)), 256, 0, (cudaStream_t)stream, a, lda, da, b, ldb, db, N, out);
   B200RL_CHECK_LAUNCH("concat2");
   return B200RL_OK;
 }

@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) scan_batch_major(const float* __restrict_
                                                         int64_t B, int64_t T, int provide_all,
                                                         int64_t ld_in, int64_t ld_out,
                                                         int64_t fv_stride) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int64_t b = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -85,6 +86,7 @@ __global__ void __launch_bounds__(128) scan_time_major(const float* __restrict__
                                                        const float* __restrict__ final_value,
                                                        float td_lambda, float* __restrict__ out,
                                                        int64_t B, int64_t T, int provide_all) {
+  pdl_prologue();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const float fin = final_value ? final_value[b] : 0.f;
@@ -111,6 +113,7 @@ __global__ void nstep_reduce_kernel(const float* __restrict__ reward,
                                     const float* __restrict__ discount, float gamma,
                                     float gamma_pow, float* __restrict__ out_reward,
                                     float* __restrict__ out_discount, int64_t B, int64_t T) {
+  pdl_prologue();
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   const int64_t n = T - 1;
@@ -136,11 +139,9 @@ int b200rl_discounted_return(const float* rewards, const float* discounts,
   if (B == 0) return B200RL_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (time_major) {
-    scan_time_major<0><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(
-        rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all);
+    B200RL_LAUNCH(scan_time_major<0>, (unsigned)((B + 127) / 128), 128, 0, st, rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all);
   } else {
-    scan_batch_major<0><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(
-        rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all, T, T, 1);
+    B200RL_LAUNCH(scan_batch_major<0>, (unsigned)((B + 7) / 8), 256, 0, st, rewards, discounts, nullptr, final_value, 0.f, out, B, T, provide_all, T, T, 1);
   }
   B200RL_CHECK_LAUNCH("discounted_return");
   return B200RL_OK;
@@ -155,11 +156,9 @@ int b200rl_gae(const float* values, const float* final_value, const float* disco
   if (B == 0) return B200RL_OK;
   cudaStream_t st = (cudaStream_t)stream;
   if (time_major) {
-    scan_time_major<1><<<(unsigned)((B + 127) / 128), 128, 0, st>>>(
-        rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1);
+    B200RL_LAUNCH(scan_time_major<1>, (unsigned)((B + 127) / 128), 128, 0, st, rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1);
   } else {
-    scan_batch_major<1><<<(unsigned)((B + 7) / 8), 256, 0, st>>>(
-        rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, T, T, 1);
+    B200RL_LAUNCH(scan_batch_major<1>, (unsigned)((B + 7) / 8), 256, 0, st, rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, T, T, 1);
   }
   B200RL_CHECK_LAUNCH("gae");
   return B200RL_OK;
@@ -173,8 +172,7 @@ int b200rl_discounted_return_ld(const float* rewards, const float* discounts,
                                 int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream) {
   B200RL_CHECK_ARG(rewards && discounts && out, "discounted_return_ld: NULL argument");
   B200RL_CHECK_ARG(B >= 1 && T >= 1 && ld_in >= T && ld_out >= T, "discounted_return_ld: sizes");
-  scan_batch_major<0><<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      rewards, discounts, nullptr, final_value, 0.f, out, B, T, 1, ld_in, ld_out, fv_stride);
+  B200RL_LAUNCH(scan_batch_major<0>, (unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream, rewards, discounts, nullptr, final_value, 0.f, out, B, T, 1, ld_in, ld_out, fv_stride);
   B200RL_CHECK_LAUNCH("discounted_return_ld");
   return B200RL_OK;
 }
@@ -184,9 +182,7 @@ int b200rl_gae_ld(const float* values, const float* final_value, const float* di
                   int64_t ld_in, int64_t ld_out, int64_t fv_stride, void* stream) {
   B200RL_CHECK_ARG(values && final_value && discounts && rewards && out_adv, "gae_ld: NULL");
   B200RL_CHECK_ARG(B >= 1 && T >= 1 && ld_in >= T && ld_out >= T, "gae_ld: sizes");
-  scan_batch_major<1><<<(unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
-      rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, ld_in, ld_out,
-      fv_stride);
+  B200RL_LAUNCH(scan_batch_major<1>, (unsigned)((B + 7) / 8), 256, 0, (cudaStream_t)stream, rewards, discounts, values, final_value, td_lambda, out_adv, B, T, 1, ld_in, ld_out, fv_stride);
   B200RL_CHECK_LAUNCH("gae_ld");
   return B200RL_OK;
 }
@@ -197,9 +193,7 @@ int b200rl_nstep_reduce(const float* reward, const float* discount, double gamma
   B200RL_CHECK_ARG(reward && discount && out_reward && out_discount, "nstep_reduce: NULL");
   B200RL_CHECK_ARG(T >= 2, "Trajectory frame count must be at least 2, but saw %lld", (long long)T);
   if (B == 0) return B200RL_OK;
-  nstep_reduce_kernel<<<(unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-      reward, discount, (float)gamma, (float)pow(gamma, (double)(T - 2)), out_reward,
-      out_discount, B, T);
+  B200RL_LAUNCH(nstep_reduce_kernel, (unsigned)((B + 255) / 256), 256, 0, (cudaStream_t)stream, reward, discount, (float)gamma, (float)pow(gamma, (double)(T - 2)), out_reward, out_discount, B, T);
   B200RL_CHECK_LAUNCH("nstep_reduce");
   return B200RL_OK;
 }

@@ -298,6 +298,8 @@ constexpr int EPI_ATOMIC = 2;  // C += acc with red.global.add (split-K without 
 struct EpiArgs {
   ConvGeom g;
   float* dx;
+  ActMask mask;     // EPI_STORE / EPI_COL2IM: multiply the input gradient by act'(mask.y)
+  float* colsum;    // EPI_ATOMIC with an MN-major B view: column sums of B (bias gradient) += here
 };
 
 // AL / BL are the fp32 operand views of nn.cu (row index = m for A, n for B).
@@ -328,7 +330,10 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
   const int64_t ke = (kb + k_per_split < K) ? kb + k_per_split : K;
   const int nkb = (int)((ke - kb + kBK - 1) / kBK);
 
+  pdl_launch_dependents();   // the next kernel of the stream may be scheduled from here on
   if (tid == 0) stamp(0);
+  float* sbias = reinterpret_cast<float*>(bars + 256);   // bias slice (EPI_STORE) / column sums
+  if (EPI == EPI_ATOMIC && tid < BN) sbias[tid] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(smem_addr(&full[s]), kProducerThreads / 32);  // one arrive per producer warp
@@ -348,6 +353,8 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // everything above touched no global memory; from here on the producing kernels must be done
+  pdl_wait();
   if (tid == 0) stamp(1);
 
   if (warp < 8) {
@@ -384,6 +391,12 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       if (BL::kKContig) gather_tile<BN>(b, b_off, b_ok, k0, ke, b_vec, tid, dst);
       else gather_tile_mn<BN>(b, n0, N, k0, ke, b_vec, tid, dst);
     };
+    // bias gradient fused into the weight-gradient GEMM: B = dY[k, n] is read by these threads
+    // anyway; in the MN-major gather every chunk of a thread covers the same 4 columns, so one
+    // float4 per thread accumulates the column sums of the CTA's K range.
+    const bool do_colsum = EPI == EPI_ATOMIC && !BL::kKContig && epi.colsum != nullptr &&
+                           blockIdx.y == 0;
+    float4 bsum = make_float4(0.f, 0.f, 0.f, 0.f);
     const int abl = TC_ABL(g_tc_variant);   // ablation probes (profiles/tc_ablate.py); 0 in production
     if (nkb > 0) {
       gather_a(kb, av);
@@ -416,6 +429,12 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
       else scatter_tile_mn<kBM, kLoA>(a_hi, a_lo, tid, cur_a);
       if (BL::kKContig) scatter_tile<BN, kLo, true>(b_hi, b_lo, tid, cur_b);
       else scatter_tile_mn<BN, kLo>(b_hi, b_lo, tid, cur_b);
+      if (do_colsum) {
+#pragma unroll
+        for (int i = 0; i < NVB; ++i) {
+          bsum.x += cur_b[i].x; bsum.y += cur_b[i].y; bsum.z += cur_b[i].z; bsum.w += cur_b[i].w;
+        }
+      }
       // No fence.proxy.async here: it lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, and the
       // MEMBAR would wait for the next block's global loads that are deliberately in flight.
       // The release-arrive below orders the stores; the MMA thread runs the proxy fence after
@@ -429,8 +448,18 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
     }
     // ===================== epilogue =====================
     if (tid == 0) stamp(2);
+    if (EPI == EPI_ATOMIC && !BL::kKContig && epi.colsum != nullptr && blockIdx.y == 0) {
+      // chunk cm = tid % (BN/4) holds columns 4cm..4cm+3; the 256/(BN/4) k-lanes of a column are
+      // combined with shared-memory atomics, one red per column goes to global memory
+      const int c4 = (tid % (BN / 4)) * 4;
+      atomicAdd(&sbias[c4 + 0], bsum.x);
+      atomicAdd(&sbias[c4 + 1], bsum.y);
+      atomicAdd(&sbias[c4 + 2], bsum.z);
+      atomicAdd(&sbias[c4 + 3], bsum.w);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (tid < BN && n0 + tid < N) atomicAdd(epi.colsum + n0 + tid, sbias[tid]);
+    }
     // bias slice of this tile -> shared memory while the last MMAs drain
-    float* sbias = reinterpret_cast<float*>(bars + 256);
     if (EPI == EPI_STORE) {
       if (tid < BN) sbias[tid] = (bias != nullptr && n0 + tid < N) ? bias[n0 + tid] : 0.f;
       asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -473,8 +502,11 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
         epi.g.d_ohow.divmod((uint32_t)m, img, rem);
         epi.g.d_ow.divmod(rem, oy, ox);
         const int64_t wc = (int64_t)epi.g.W * epi.g.C;
-        float* base = epi.dx + ((int64_t)img * epi.g.H + (int64_t)oy * epi.g.stride) * wc +
-                      (int64_t)ox * epi.g.stride * epi.g.C;
+        const int64_t in_off = (int64_t)oy * epi.g.stride * wc + (int64_t)ox * epi.g.stride * epi.g.C;
+        float* base = epi.dx + (int64_t)img * epi.g.H * wc + in_off;
+        // act'(X) of the layer that produced the conv input: the scatter-add is linear, so every
+        // contribution is masked on its way out (X is read at the destination index)
+        const float* ybase = epi.mask.y ? epi.mask.y + (int64_t)img * epi.mask.ld + in_off : nullptr;
 #pragma unroll
         for (int j = 0; j < G; j += 4) {
           const int64_t kidx = nb + j;
@@ -482,9 +514,15 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
           uint32_t ky, rr;
           epi.g.d_kwc.divmod((uint32_t)kidx, ky, rr);
           float* dst = base + (int64_t)ky * wc + rr;
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst),
-                       "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])),
-                       "f"(__uint_as_float(r[j + 2])), "f"(__uint_as_float(r[j + 3]))
+          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                 __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          if (ybase) {
+            const float4 y = *reinterpret_cast<const float4*>(ybase + (int64_t)ky * wc + rr);
+            v.x = dact(y.x, v.x, epi.mask.act); v.y = dact(y.y, v.y, epi.mask.act);
+            v.z = dact(y.z, v.z, epi.mask.act); v.w = dact(y.w, v.w, epi.mask.act);
+          }
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x),
+                       "f"(v.y), "f"(v.z), "f"(v.w)
                        : "memory");
         }
         continue;
@@ -513,6 +551,7 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
         if (splits == 1 && nb + j < N && m < M) {
           x += sbias[c + j];
           x = apply_act(x, act);
+          if (!vec_out && epi.mask.y) x = dact(epi.mask.y[m * epi.mask.ld + nb + j], x, epi.mask.act);
           if (beta) x += out[m * N + nb + j];
         }
         v[j] = x;
@@ -540,8 +579,16 @@ __global__ void __launch_bounds__(kThreads, (BN <= 64 ? 2 : 1)) tc_gemm_kernel(c
         const int row = warp * 16 + rr + lane / LPR;
         const int64_t gm = m0 + row;
         if (gm < M && n0 + col < N) {
-          const float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) +
-                                                            row * kStagePitch + col);
+          float4 t = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(smem) +
+                                                      row * kStagePitch + col);
+          if (splits == 1 && epi.mask.y) {   // coalesced read of the producing layer's output
+            const float* yp = epi.mask.y + gm * epi.mask.ld + n0 + col;
+            const bool yv = (epi.mask.ld & 3) == 0 && ((uintptr_t)epi.mask.y & 15) == 0;
+            const float4 y = yv ? *reinterpret_cast<const float4*>(yp)
+                                : make_float4(yp[0], yp[1], yp[2], yp[3]);
+            t.x = dact(y.x, t.x, epi.mask.act); t.y = dact(y.y, t.y, epi.mask.act);
+            t.z = dact(y.z, t.z, epi.mask.act); t.w = dact(y.w, t.w, epi.mask.act);
+          }
           *reinterpret_cast<float4*>(out + gm * N + n0 + col) = t;
         }
       }

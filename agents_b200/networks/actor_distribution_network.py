@@ -111,10 +111,11 @@ class ActorDistributionNetwork(network.Network):
     _lib.call('b200rl_normal_proj_bwd', _lib.ptr(m_raw), _lib.ptr(self._std.bias),
               _lib.ptr(self._amin), _lib.ptr(self._amax), _lib.ptr(dloc), _lib.ptr(dscale), n,
               self.num_actions, _lib.ptr(dm), _lib.ptr(ds_part), _lib.stream())
+    grads = super().backward(tape, dm)      # zeroes the flat gradient, then accumulates
     ws, nb = workspace.get(m_raw.device)
     _lib.call('b200rl_colsum', _lib.ptr(ds_part), None, 0, n, self.num_actions, 1.0,
               _lib.ptr(self._std.d_bias), _lib.ptr(ws), nb, _lib.stream())
-    return super().backward(tape, dm)
+    return grads
 
   def __call__(self, observation, step_type=None, network_state=(), training=False):
     return self.distribution_params(observation), network_state

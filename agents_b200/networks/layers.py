@@ -168,9 +168,12 @@ class Dense(Layer):
               _lib.stream())
     return dz
 
-  def backward_parts(self, x, dz, need_dx, need_dw):
+  def backward_parts(self, x, dz, need_dx, need_dw, x_act=_lib.ACT_NONE, accumulate=0):
     """Input gradient and/or parameter gradients from dz (either half may be skipped, so that the
-    two halves can run on different streams)."""
+    two halves can run on different streams).  `x_act`: activation code of the layer that
+    produced `x`; the returned input gradient is then w.r.t. that layer's pre-activation (the
+    act' factor is applied in the GEMM epilogue).  `accumulate`: add into the gradient views
+    (the Network zeroes its flat gradient buffer once per backward pass)."""
     x, ldx = _batch_strided(x, self.in_features)
     m = x.shape[0]
     dx = torch.empty((m, self.in_features), dtype=torch.float32, device=x.device) if need_dx else None
@@ -178,11 +181,11 @@ class Dense(Layer):
     _lib.call('b200rl_dense_bwd', _lib.dptr(x), ldx, _lib.ptr(self.kernel), _lib.ptr(dz),
               _lib.ptr(dx), _lib.ptr(self.d_kernel) if need_dw else None,
               _lib.ptr(self.d_bias) if need_dw else None, m, self.in_features,
-              self.units, 0, _lib.ptr(ws), nb, _lib.stream())
+              self.units, int(accumulate), int(x_act), _lib.ptr(ws), nb, _lib.stream())
     return dx
 
-  def backward(self, x, y, dy, need_dx, need_dw=True):
-    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw)
+  def backward(self, x, y, dy, need_dx, need_dw=True, x_act=_lib.ACT_NONE):
+    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw, x_act)
 
 
 class Conv2D(Layer):
@@ -266,7 +269,7 @@ class Conv2D(Layer):
               _lib.stream())
     return dz
 
-  def backward_parts(self, x, dz, need_dx, need_dw):
+  def backward_parts(self, x, dz, need_dx, need_dw, x_act=_lib.ACT_NONE, accumulate=0):
     x, bstride, is_u8 = self._input(x)
     g = self._geom(x)
     g.x_batch_stride = bstride
@@ -279,9 +282,9 @@ class Conv2D(Layer):
     _lib.call('b200rl_conv2d_bwd', _lib.dptr(x), int(is_u8), float(self.pre_divisor or 1.0),
               _lib.ptr(self.kernel), _lib.ptr(dz), _lib.ptr(dx),
               _lib.ptr(self.d_kernel) if need_dw else None,
-              _lib.ptr(self.d_bias) if need_dw else None, ctypes.byref(g), 0, _lib.ptr(ws), nb,
-              _lib.stream())
+              _lib.ptr(self.d_bias) if need_dw else None, ctypes.byref(g), int(accumulate),
+              int(x_act), _lib.ptr(ws), nb, _lib.stream())
     return dx
 
-  def backward(self, x, y, dy, need_dx, need_dw=True):
-    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw)
+  def backward(self, x, y, dy, need_dx, need_dw=True, x_act=_lib.ACT_NONE):
+    return self.backward_parts(x, self.backward_act(y, dy), need_dx, need_dw, x_act)

@@ -208,25 +208,54 @@ class Network(object):
     w.r.t. their action input); need_param_grads=False skips the weight gradients (dense only).
     Returns flat_grads, or (flat_grads, d_input) when need_input_grad."""
     first = next(i for i, (l, _, _) in enumerate(tape) if l.has_params)
-    # Inside a captured graph the parameter gradients (dW GEMM + bias column sum) of every
+    # Inside a captured graph the parameter gradients (dW GEMM + fused bias column sums) of every
     # layer are forked onto a side stream: only the dX chain stays on the critical path.
     side = _side_stream(self._device) if (
         _BWD_OVERLAP and need_param_grads and torch.cuda.is_current_stream_capturing()) else None
     main = torch.cuda.current_stream() if side is not None else None
+    # The flat gradient is zeroed ONCE and every layer accumulates into its views (split-K weight
+    # gradients and the fused bias sums are red.global.add epilogues): one fill instead of one
+    # memset node per layer.
+    zeroed = not need_param_grads
+    if need_param_grads and side is None:
+      self._grads.zero_()
+      zeroed = True
+
+    def producer_act(i):
+      """Activation code of the layer whose output is tape[i]'s input (Flatten is a view)."""
+      j = i - 1
+      while j >= 0 and isinstance(tape[j][0], layers_lib.Flatten):
+        j -= 1
+      if j < 0 or not hasattr(tape[j][0], 'backward_parts'):
+        return _ACT_NONE
+      return tape[j][0]._act
+
+    dy_is_preact = False     # dy already carries act' of the layer it is handed to
     for i in range(len(tape) - 1, -1, -1):
       l, x, y = tape[i]
       need_dx = need_input_grad or i > first
-      if side is not None and hasattr(l, 'backward_parts'):
-        dz = l.backward_act(y, dy)
+      if not hasattr(l, 'backward_parts'):
+        dy = l.backward(x, y, dy, need_dx=need_dx)       # Flatten: reshape, flag carries through
+        continue
+      dz = dy.contiguous() if dy_is_preact else l.backward_act(y, dy)
+      x_act = producer_act(i) if need_dx and _FUSE_ACT_BWD else _ACT_NONE
+      if side is not None:
         side.wait_stream(main)                   # dz (and everything before it) is ready
         dz.record_stream(side)
         with torch.cuda.stream(side), workspace.slot(1):
-          l.backward_parts(x, dz, need_dx=False, need_dw=True)
-        dy = l.backward_parts(x, dz, need_dx=True, need_dw=False) if need_dx else None
-      elif not need_param_grads and isinstance(l, layers_lib.Dense):
-        dy = l.backward(x, y, dy, need_dx=need_dx, need_dw=False)
+          if not zeroed:
+            self._grads.zero_()
+            zeroed = True
+          l.backward_parts(x, dz, need_dx=False, need_dw=True, accumulate=1)
+        dy = l.backward_parts(x, dz, need_dx=True, need_dw=False, x_act=x_act) if need_dx else None
+      elif not need_param_grads:
+        if isinstance(l, layers_lib.Dense):
+          dy = l.backward_parts(x, dz, need_dx=need_dx, need_dw=False, x_act=x_act)
+        else:
+          raise NotImplementedError('need_param_grads=False is only supported for Dense stacks.')
       else:
-        dy = l.backward(x, y, dy, need_dx=need_dx)
+        dy = l.backward_parts(x, dz, need_dx=need_dx, need_dw=True, x_act=x_act, accumulate=1)
+      dy_is_preact = x_act != _ACT_NONE
     if side is not None:
       main.wait_stream(side)
     elif _BWD_OVERLAP and not torch.cuda.is_current_stream_capturing():
@@ -238,6 +267,9 @@ class Network(object):
 
 
 _BWD_OVERLAP = os.environ.get('B200RL_BWD_OVERLAP', '1') != '0'
+# act'(x) of the producing layer folded into the consumer's dX epilogue (0: separate act_bwd pass)
+_FUSE_ACT_BWD = os.environ.get('B200RL_FUSE_ACT_BWD', '1') != '0'
+_ACT_NONE = 0
 _SIDE_STREAMS = {}
 
 

@@ -36,6 +36,16 @@ def _agent_state_tensors(agent):
   la = getattr(agent, '_log_alpha', None)
   if isinstance(la, torch.Tensor):
     out['_log_alpha'] = la
+  # PPO: streaming normalisers (tf.Module variables of the agent in the reference, so they are
+  # checkpointed and mirrored with it) and the adaptive KL coefficient (ppo_agent.py:341-343)
+  for name in ('_observation_normalizer', '_reward_normalizer'):
+    norm = getattr(agent, name, None)
+    if norm is not None and hasattr(norm, 'variables'):
+      for i, v in enumerate(norm.variables):
+        out[f'{name}/{i}'] = v
+  beta = getattr(agent, '_adaptive_kl_beta', None)
+  if isinstance(beta, torch.Tensor):
+    out['_adaptive_kl_beta'] = beta
   upd = getattr(agent, '_update_target', None)       # Periodically counter (a tf.Variable there)
   if isinstance(getattr(upd, '_counter', None), torch.Tensor):
     out['_update_target/counter'] = upd._counter
@@ -92,6 +102,7 @@ class Learner(object):
       agent._grad_sync = self.strategy.all_reduce_sum
       if hasattr(agent, '_stat_sync'):
         agent._stat_sync = self.strategy.all_reduce_sum
+        agent._replica_rank = self.strategy.rank
       for t in _agent_state_tensors(agent).values():   # mirror rank 0 (MirroredStrategy semantics)
         self.strategy.broadcast(t, src=0)
     self._last_checkpoint_step = None

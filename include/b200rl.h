@@ -53,6 +53,12 @@ const char* b200rl_last_error(void);
 int b200rl_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t b200rl_launch_count(void);
+/* Programmatic dependent launch: when enabled (or B200RL_PDL=1 in the environment) every kernel
+ * is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so inside a captured step
+ * (common.function, utils/common.py:128 in the reference) the next node's launch overlaps the
+ * running one; every kernel orders itself with griddepcontrol.wait. */
+int b200rl_set_pdl(int enabled);
+int b200rl_get_pdl(void);
 
 /* ------------------------------------------------------------------------------------
  * Ring storage — replaces Table (replay_buffers/table.py:32-137) + the variables of
@@ -191,15 +197,43 @@ int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt, const float* nex
  * sum(loss*w) / (T * global_batch), utils/common.py:1400-1476).  The current policy is a diagonal
  * Normal(loc, scale) given as [N, A] views with row stride ld_ls; gradients are written with row
  * stride ld_g.  clip_eps <= 0, value_clip <= 0, logp_clip <= 0 disable the respective clipping.
- * losses[5] = {policy_gradient, value_estimation (x vf_coef), entropy_regularization (x ent_coef),
- * clip_fraction, sum of the three losses}. */
+ * losses[6] = {policy_gradient, value_estimation (x vf_coef), entropy_regularization (x ent_coef),
+ * clip_fraction, total (without l2), kl_penalty}.
+ * kl (NULL: no KL penalty, what PPOClipAgent configures, ppo_clip_agent.py:226-232): the
+ * behaviour policy's Normal(old_loc, old_scale) and the device scalars written by
+ * b200rl_ppo_kl_terms; the gradient of kl_cutoff_loss + adaptive_kl_loss (ppo_agent.py:1514-1630)
+ * is added to dloc/dscale and their sum to the total. */
+typedef struct {
+  const float* old_loc;   /* device [N, A], row stride ld_old */
+  const float* old_scale;
+  int64_t ld_old;
+  const float* terms;     /* device float[3] from b200rl_ppo_kl_terms */
+  float grad_scale;       /* d(mean_kl)/d(sum_n w_n kl_n) = 1 / N_global */
+} b200rl_ppo_kl_t;
 int b200rl_ppo_loss(const float* loc, const float* scale, int64_t ld_ls, const float* action,
                     const float* old_logp, const float* adv, const float* ret, const float* v,
                     const float* v_old, const float* w, int64_t N, int64_t A, int64_t T,
                     float global_batch, float clip_eps, float value_clip, float vf_coef,
                     float ent_coef, float logp_clip, float* losses, float* dloc, float* dscale,
-                    int64_t ld_g, float* dv, int32_t* nan_flag, void* workspace,
-                    int64_t ws_bytes, void* stream);
+                    int64_t ld_g, float* dv, int32_t* nan_flag, const b200rl_ppo_kl_t* kl,
+                    void* workspace, int64_t ws_bytes, void* stream);
+/* out_sum = out_scale * sum_n w_n * KL(Normal(old_loc, old_scale)_n || Normal(loc, scale)_n), the
+ * KL summed over action dims (ppo_utils.nested_kl_divergence, ppo_utils.py:194-227; per-dimension
+ * closed form of tfp Normal); out_kl (optional) keeps the weighted per-element values
+ * (kl_penalty_loss, ppo_agent.py:1613-1617).  w may be NULL. */
+int b200rl_ppo_kl(const float* loc, const float* scale, int64_t ld, const float* old_loc,
+                  const float* old_scale, int64_t ld_old, const float* w, int64_t N, int64_t A,
+                  float out_scale, float* out_kl, float* out_sum, void* workspace,
+                  int64_t ws_bytes, void* stream);
+/* terms[3] = {kl_cutoff_loss = coef * max(mean_kl - factor*target, 0)^2 (ppo_agent.py:1514-1539;
+ * 0 when factor <= 0), adaptive_kl_loss = beta * mean_kl (:1541-1558; beta_dev NULL -> 0), and the
+ * derivative of their sum w.r.t. mean_kl}. */
+int b200rl_ppo_kl_terms(const float* mean_kl_dev, const float* beta_dev, float kl_cutoff_factor,
+                        float adaptive_kl_target, float kl_cutoff_coef, float* terms_dev,
+                        void* stream);
+/* update_adaptive_kl_beta (ppo_agent.py:1632-1675) on the device-resident beta. */
+int b200rl_ppo_kl_beta_update(const float* mean_kl_dev, float* beta_dev, float adaptive_kl_target,
+                              float adaptive_kl_tolerance, void* stream);
 /* log-prob of actions under Normal(loc, scale), summed over action dims (common.py:682-717). */
 int b200rl_normal_logp(const float* loc, const float* scale, int64_t ld, const float* action,
                        int64_t N, int64_t A, float* out, void* stream);
@@ -302,10 +336,15 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
                      int64_t ws_bytes, void* stream);
 /* Given dY[M,N] (already multiplied by act'), compute dX[M,K] (optional, NULL to skip),
  * dW[K,N] (optional) and db[N] (optional).  accumulate!=0 adds into dW/db instead of
- * overwriting. */
+ * overwriting.  x_act: activation code of the layer whose OUTPUT is X (B200RL_ACT_NONE when X is
+ * a raw input): dX is then multiplied by act'(X) in the GEMM epilogue, i.e. it is the gradient
+ * w.r.t. that layer's pre-activation and no b200rl_act_bwd pass is needed (Keras composes
+ * Dense(activation=...) the same way, networks/encoding_network.py:287-300).  In tensor-core
+ * mode db is accumulated by the operand producers of the dW GEMM (no separate column-sum
+ * launches; B200RL_FUSE_BIAS_GRAD=0 restores them). */
 int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
                      float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
-                     void* workspace, int64_t ws_bytes, void* stream);
+                     int x_act, void* workspace, int64_t ws_bytes, void* stream);
 /* dZ = dY * act'(Y) element-wise (in place allowed). */
 int b200rl_act_bwd(const float* Y, const float* dY, float* dZ, int64_t n, int act,
                    void* stream);
@@ -322,10 +361,12 @@ int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt
                       const float* bias, float* Y, const b200rl_conv_t* g, int act,
                       void* workspace, int64_t ws_bytes, void* stream);
 /* dX, dW and db may each be NULL (that gradient is skipped), so the parameter gradients and the
- * input gradient of one layer can be issued on different streams. */
+ * input gradient of one layer can be issued on different streams.  x_act as in
+ * b200rl_dense_bwd: the col2im scatter-add is linear, so act'(X) is applied to every
+ * contribution at its destination element. */
 int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
                       const float* dY, float* dX, float* dW, float* db,
-                      const b200rl_conv_t* g, int accumulate, void* workspace,
+                      const b200rl_conv_t* g, int accumulate, int x_act, void* workspace,
                       int64_t ws_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------

@@ -3,10 +3,14 @@
 Follows agents/ppo/ppo_agent.py: _normalize_advantages :100-110, compute_advantages :440-479,
 get_loss :481-615, compute_return_and_advantage :617-719, _preprocess :721-807, _train :834-1076,
 entropy_regularization_loss :1159-1201, value_estimation_loss :1203-1327,
-policy_gradient_loss :1329-1512; agents/ppo/ppo_utils.py:35-59 (make_trajectory_mask);
+policy_gradient_loss :1329-1512, kl_cutoff_loss :1514-1539, adaptive_kl_loss :1541-1558,
+kl_penalty_loss :1586-1630, update_adaptive_kl_beta :1632-1675;
+agents/ppo/ppo_utils.py:35-59 (make_trajectory_mask), :194-227 (nested_kl_divergence);
 utils/common.py:682-755 (log_probability / entropy summed over action dims), :883-895
 (get_episode_mask), :1400-1476 (aggregate_losses); utils/tensor_normalizer.py:134-205,288-470.
-The Normal log-prob / entropy formulas are TFP's closed forms.
+The Normal log-prob / entropy / KL formulas are TFP's closed forms (tensorflow_probability is an
+un-vendored dependency; Normal.kl_divergence is `_kl_normal_normal` in
+tfp/distributions/normal.py: 0.5*sqdiff(mu_a/s_b, mu_b/s_b) + 0.5*expm1(2d) - d, d = log s_a - log s_b).
 """
 import numpy as np
 
@@ -27,6 +31,43 @@ def normal_log_prob(loc, scale, action):
 
 def normal_entropy(scale):
   return np.sum(0.5 + 0.5 * LOG2PI + np.log(scale), axis=-1).astype(f32)
+
+
+def normal_kl(loc_a, scale_a, loc_b, scale_b):
+  """sum_k KL(N(loc_a, scale_a) || N(loc_b, scale_b)) over the action dims
+  (ppo_utils.nested_kl_divergence :194-227 reduces the non-batch dims)."""
+  d = (np.log(scale_a) - np.log(scale_b)).astype(f32)
+  z = (loc_a / scale_b - loc_b / scale_b).astype(f32)
+  return np.sum(f32(0.5) * z * z + f32(0.5) * np.expm1(f32(2) * d) - d, axis=-1).astype(f32)
+
+
+def kl_cutoff_loss(kl, kl_cutoff_factor, adaptive_kl_target, kl_cutoff_coef):
+  """:1514-1539."""
+  if kl_cutoff_factor <= 0:
+    return f32(0)
+  cutoff = f32(kl_cutoff_factor * adaptive_kl_target)
+  over = np.maximum(np.mean(kl, dtype=f32) - cutoff, f32(0))
+  return f32(f32(kl_cutoff_coef) * over * over)
+
+
+def adaptive_kl_loss(kl, beta):
+  """:1541-1558 (beta None -> 0)."""
+  if beta is None:
+    return f32(0)
+  return f32(f32(beta) * np.mean(kl, dtype=f32))
+
+
+def update_adaptive_kl_beta(beta, kl, adaptive_kl_target, adaptive_kl_tolerance):
+  """:1632-1675; returns the new beta."""
+  if beta is None:
+    return None
+  mean_kl = np.mean(kl, dtype=f32)
+  factor = f32(1)
+  if mean_kl < f32(adaptive_kl_target) * f32(1.0 - adaptive_kl_tolerance):
+    factor = f32(1.0 / 1.5)
+  elif mean_kl > f32(adaptive_kl_target) * f32(1.0 + adaptive_kl_tolerance):
+    factor = f32(1.5)
+  return f32(np.clip(f32(beta) * factor, f32(10e-16), f32(10e16)))
 
 
 def aggregate(per_example, weights, global_batch=None):
@@ -155,7 +196,10 @@ class PPOOracle(object):
   def __init__(self, actor, std_bias, value, amin, amax, optimizer, num_epochs=25,
                clip_eps=0.2, vf_coef=0.5, ent_coef=0.0, gamma=0.99, lam=0.95, value_clip=0.0,
                logp_clip=0.0, gradient_clipping=None, normalize_rewards=False,
-               reward_norm_clipping=10.0, use_gae=True, use_td_lambda_return=False):
+               reward_norm_clipping=10.0, use_gae=True, use_td_lambda_return=False,
+               kl_cutoff_factor=0.0, kl_cutoff_coef=0.0, initial_adaptive_kl_beta=0.0,
+               adaptive_kl_target=0.0, adaptive_kl_tolerance=0.0, normalize_observations=False,
+               obs_dim=None):
     self.actor, self.value, self.std_bias = actor, value, np.asarray(std_bias, f32)
     self.amin, self.amax = np.asarray(amin, f32), np.asarray(amax, f32)
     self.opt = optimizer
@@ -166,6 +210,17 @@ class PPOOracle(object):
     self.reward_normalizer = StreamingNormalizer(()) if normalize_rewards else None
     self.reward_norm_clipping = reward_norm_clipping
     self.train_step_counter = 0
+    self.kl_cutoff_factor, self.kl_cutoff_coef = kl_cutoff_factor, kl_cutoff_coef
+    self.initial_beta = initial_adaptive_kl_beta
+    self.beta = f32(initial_adaptive_kl_beta) if initial_adaptive_kl_beta > 0 else None   # :339-345
+    self.kl_target, self.kl_tol = adaptive_kl_target, adaptive_kl_tolerance
+    # observation normaliser: applied by the policy before both networks (ppo_policy.py)
+    self.obs_normalizer = StreamingNormalizer((obs_dim,)) if normalize_observations else None
+
+  def norm_obs(self, obs):
+    if self.obs_normalizer is None:
+      return obs
+    return self.obs_normalizer.normalize(obs)       # defaults: clip 5, centred (:134-205)
 
   # -- policy head -----------------------------------------------------------------------------
   def dist(self, obs, keep=False):
@@ -182,7 +237,7 @@ class PPOOracle(object):
     """_preprocess (:721-807): value preds on all T steps, returns / advantages padded with 0."""
     B, T = exp['reward'].shape
     obs = exp['observation']
-    vp = self.value.forward(obs.reshape(B * T, -1)).reshape(B, T)
+    vp = self.value.forward(self.norm_obs(obs.reshape(B * T, -1))).reshape(B, T)
     reward = exp['reward'][:, :-1]
     if self.reward_normalizer is not None:                                     # :651-654
       reward = self.reward_normalizer.normalize(reward, center_mean=False,
@@ -193,7 +248,8 @@ class PPOOracle(object):
     pad = np.zeros((B, 1), f32)
     return vp, np.concatenate([ret, pad], 1), np.concatenate([adv, pad], 1)
 
-  def loss_and_grads(self, obs, action, old_logp, ret, adv_n, v_old, w, B, T, global_batch=None):
+  def loss_and_grads(self, obs, action, old_logp, ret, adv_n, v_old, w, B, T, global_batch=None,
+                     old_loc=None, old_scale=None):
     """get_loss (:481-615) + hand-written backward. All inputs flattened to N = B*T."""
     N = B * T
     gb = f32(global_batch or B)
@@ -209,7 +265,22 @@ class PPOOracle(object):
     ve = value_estimation_loss(v.reshape(sh), ret.reshape(sh), w.reshape(sh), self.vf_coef,
                                self.value_clip, None if v_old is None else v_old.reshape(sh), gb)
     en = entropy_regularization_loss(ent.reshape(sh), w.reshape(sh), self.ent_coef, gb)
-    total = f32(pg + ve + en)
+    use_kl = not (self.initial_beta == 0 and self.kl_cutoff_factor == 0)           # :586
+    klp, g_kl = f32(0), np.zeros(N, f32)
+    if use_kl:                                                                     # :1586-1630
+      kl = (normal_kl(old_loc, old_scale, loc, scale) * w).astype(f32)
+      cut = kl_cutoff_loss(kl, self.kl_cutoff_factor, self.kl_target, self.kl_cutoff_coef)
+      ada = adaptive_kl_loss(kl, self.beta)
+      klp = f32(cut + ada)
+      mean_kl = np.mean(kl, dtype=f32)
+      dmean = f32(0)
+      if self.kl_cutoff_factor > 0:
+        dmean += f32(2 * self.kl_cutoff_coef) * np.maximum(
+            mean_kl - f32(self.kl_cutoff_factor * self.kl_target), f32(0))
+      if self.beta is not None:
+        dmean += f32(self.beta)
+      g_kl = (dmean * w / f32(N)).astype(f32)
+    total = f32(pg + ve + en + klp)
     # ---- backward (derived independently of csrc/ppo.cu; checked against autograd in tests)
     lp, dlp = logp, np.ones(N, f32)
     if self.logp_clip > 0:
@@ -230,6 +301,10 @@ class PPOOracle(object):
     inv = 1.0 / scale
     dloc = (g_logp[:, None] * d * inv * inv).astype(f32)
     dscale = (g_logp[:, None] * (d * d * inv ** 3 - inv) + g_ent[:, None] * inv).astype(f32)
+    if use_kl:       # d KL(old || new) / d(new loc, new scale)
+      dm = old_loc - loc
+      dloc = (dloc + g_kl[:, None] * (-dm * inv * inv)).astype(f32)
+      dscale = (dscale + g_kl[:, None] * (inv - (dm * dm + old_scale ** 2) * inv ** 3)).astype(f32)
     err = (ret - v) ** 2
     derr = -2 * (ret - v)
     if self.value_clip > 0:
@@ -244,7 +319,7 @@ class PPOOracle(object):
     sig = 1.0 / (1.0 + np.exp(-self.std_bias))
     dstd = (dscale * sig).sum(axis=0).astype(f32)
     grads = self.actor.backward(atape, dm_raw) + [dstd] + self.value.backward(vtape, dv[:, None])
-    return dict(loss=total, pg=pg, ve=ve, ent=en, clip_fraction=clip_frac), grads
+    return dict(loss=total, pg=pg, ve=ve, ent=en, clip_fraction=clip_frac, kl=klp), grads
 
   def preprocess_sequence(self, exp):
     """_preprocess_sequence (:809-832) for compute_value_and_advantage_in_train=False: value
@@ -280,16 +355,25 @@ class PPOOracle(object):
     old_loc, old_scale = exp['loc'].reshape(B * T, A), exp['scale'].reshape(B * T, A)
     old_logp = normal_log_prob(old_loc, old_scale, action)                      # :867-869
     adv_n = normalize_advantages(adv)                                           # :893-895
-    obs = exp['observation'].reshape(B * T, -1)
+    raw_obs = exp['observation'].reshape(B * T, -1)
+    obs = self.norm_obs(raw_obs)
     infos = []
     for _ in range(self.num_epochs):                                            # :925-967
       info, grads = self.loss_and_grads(obs, action, old_logp, ret.reshape(-1), adv_n.reshape(-1),
-                                        vp.reshape(-1), w.reshape(-1), B, T)
+                                        vp.reshape(-1), w.reshape(-1), B, T,
+                                        old_loc=old_loc, old_scale=old_scale)
       if self.gradient_clipping:
         grads, _ = optim.clip_by_global_norm(grads, self.gradient_clipping)
       self.opt.apply(self.params(), grads)
       self.train_step_counter += 1
       infos.append(info)
-    if self.reward_normalizer is not None and update_normalizers:               # :991-993
-      self.reward_normalizer.update(exp['reward'])
+    if self.initial_beta > 0:                                                   # :978-989
+      loc, scale = self.dist(obs)
+      kl = (normal_kl(old_loc, old_scale, loc, scale) * w.reshape(-1)).astype(f32)
+      self.beta = update_adaptive_kl_beta(self.beta, kl, self.kl_target, self.kl_tol)
+    if update_normalizers:                                                      # :991-993
+      if self.obs_normalizer is not None:
+        self.obs_normalizer.update(raw_obs)
+      if self.reward_normalizer is not None:
+        self.reward_normalizer.update(exp['reward'])
     return infos

@@ -89,6 +89,26 @@ def test_loss_masked_actions_golden(cuda, agent_class):  # :483-561 -> 23.75
   np.testing.assert_allclose(agent.loss(exp).loss.item(), 23.75, rtol=1e-6)
 
 
+def test_d3qn_goldens(cuda):
+  """D3qnAgent (dqn_agent.py:704-753): the unmasked goldens like DDQN, and 26.0 on the masked
+  case because its argmax ignores the action constraint (dqn_agent_test.py:483-561, :556)."""
+  tss, acts = _specs()
+  two = [[[1, 2], [3, 4]], [[5, 6], [7, 8]]]
+  agent = dqn_agent.D3qnAgent(tss, acts, q_network=_dummy_net(cuda), optimizer=None)
+  agent.initialize()
+  loss = agent.loss(_exp(cuda, two, [0, 1], [[10, 20]] * 2, [[.9, .9]] * 2)).loss
+  np.testing.assert_allclose(loss.item(), 26.0, rtol=1e-6)
+  loss = agent.loss(_exp(cuda, [two[0], [[-5, 6], [-7, 8]]], [0, 1], [[10, 20]] * 2, [[.9, .9]] * 2)).loss
+  np.testing.assert_allclose(loss.item(), 9.8, rtol=1e-6)
+  tss, acts = _specs(with_mask=True)
+  agent = dqn_agent.D3qnAgent(tss, acts, q_network=_dummy_net(cuda), optimizer=None,
+                              observation_and_action_constraint_splitter=lambda x: (x[0], x[1]))
+  agent.initialize()
+  exp = _exp(cuda, two, [0, 1], [[10, 20]] * 2, [[.9, .9]] * 2,
+             masks=[[[1, 1], [1, 1]], [[0, 1], [1, 0]]])
+  np.testing.assert_allclose(agent.loss(exp).loss.item(), 26.0, rtol=1e-6)
+
+
 def test_sequence_length_validation(cuda):
   tss, acts = _specs()
   agent = dqn_agent.DqnAgent(tss, acts, q_network=_dummy_net(cuda), optimizer=None)

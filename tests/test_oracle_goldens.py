@@ -289,6 +289,12 @@ def test_dqn_loss_masked_actions():  # :483-561 -> 23.75
                       np.array([[10, 0], [20, 0]], f32), np.array([[.9, 1], [.9, 1]], f32),
                       next_mask=np.array([[0, 1], [1, 0]]))
   np.testing.assert_allclose(out['loss'], 23.75, rtol=1e-6)
+  # D3qnAgent selects with a raw argmax of the online network (dqn_agent.py:731), so the same
+  # case without the mask is what the reference expects for it: 26.0 (dqn_agent_test.py:556)
+  out = odqn.dqn_loss(net.forward(obs0), net.forward(obsn), net.forward(obsn), [0, 1], [0, 0],
+                      np.array([[10, 0], [20, 0]], f32), np.array([[.9, 1], [.9, 1]], f32),
+                      next_mask=None)
+  np.testing.assert_allclose(out['loss'], 26.0, rtol=1e-6)
 
 
 def test_huber_matches_test_comment():  # dqn_agent_test.py:205-213 ("Huber loss subtracts 0.5")

@@ -97,6 +97,8 @@ def _make_oracle(rng, obs_dim=5, A=3, hidden=(8, 6), **kw):
       n_in = h
     layers.append(dict(kind='dense', w=(rng.randn(n_in, out) * scale_last).astype(f32), b=np.zeros(out, f32), act=None))
     return onn.Sequential(layers)
+  if kw.get('normalize_observations'):
+    kw['obs_dim'] = obs_dim
   return oppo.PPOOracle(mlp(A, .3), (rng.randn(A) * .2).astype(f32), mlp(1, .3), -np.ones(A, f32) * 2,
                         np.ones(A, f32) * 2, ooptim.AdamTF(1e-3, eps=1e-7), **kw)
 
@@ -156,3 +158,99 @@ def test_oracle_train_runs_epochs():
   infos = orc.train(exp)
   assert len(infos) == 3 == orc.train_step_counter
   assert all(np.isfinite(i['loss']) for i in infos) and infos[0]['loss'] != infos[-1]['loss']
+
+
+# ---- KL penalty (ppo_agent.py:1514-1690) ---------------------------------------------------------
+def test_kl_cutoff_loss_golden():  # ppo_agent_test.py:1045-1078: coef * (0.74 - 0.5)^2, 0 when coef 0
+  kl = np.array([[1.5, -0.5, 6.5, -1.5, -2.3]], f32)
+  for coef in (0.0, 30.0):
+    got = oppo.kl_cutoff_loss(kl, kl_cutoff_factor=5.0, adaptive_kl_target=0.1, kl_cutoff_coef=coef)
+    np.testing.assert_allclose(got, coef * 0.24 ** 2, rtol=1e-5)
+  assert oppo.kl_cutoff_loss(kl, 0.0, 0.1, 30.0) == 0.0                       # :1518-1519
+
+
+def test_adaptive_kl_loss_and_beta_update_goldens():  # :1080-1164
+  beta = f32(1.0)
+  # :1113-1124 loss moves with beta; :1149-1164 beta 1.0 -> 1.0 -> 1.5 -> 1.0
+  assert oppo.adaptive_kl_loss(np.array([10.0], f32), beta) == 10.0
+  beta = oppo.update_adaptive_kl_beta(beta, np.array([10.0], f32), 10.0, 0.5)
+  assert beta == 1.0
+  beta = oppo.update_adaptive_kl_beta(beta, np.array([100.0], f32), 10.0, 0.5)
+  assert beta == 1.5
+  assert oppo.adaptive_kl_loss(np.array([100.0], f32), beta) > 100.0
+  beta = oppo.update_adaptive_kl_beta(beta, np.array([1.0], f32), 10.0, 0.5)
+  np.testing.assert_allclose(beta, 1.0, rtol=1e-6)
+  assert oppo.update_adaptive_kl_beta(None, np.array([1.0], f32), 10.0, 0.5) is None
+  assert oppo.adaptive_kl_loss(np.array([1.0], f32), None) == 0.0
+
+
+def test_normal_kl_matches_torch_distributions():
+  rng = np.random.RandomState(5)
+  la, lb = rng.randn(7, 3).astype(f32), rng.randn(7, 3).astype(f32)
+  sa, sb = (rng.rand(7, 3) + .3).astype(f32), (rng.rand(7, 3) + .3).astype(f32)
+  want = torch.distributions.kl_divergence(torch.distributions.Normal(torch.tensor(la), torch.tensor(sa)),
+                                           torch.distributions.Normal(torch.tensor(lb), torch.tensor(sb))).sum(-1)
+  np.testing.assert_allclose(oppo.normal_kl(la, sa, lb, sb), want.numpy(), rtol=2e-5, atol=1e-6)
+
+
+def test_oracle_kl_penalty_backward_matches_autograd():
+  rng = np.random.RandomState(7)
+  B, T, A, D = 4, 5, 3, 5
+  kw = dict(kl_cutoff_factor=2.0, kl_cutoff_coef=50.0, initial_adaptive_kl_beta=1.3,
+            adaptive_kl_target=0.01, adaptive_kl_tolerance=0.3)
+  orc = _make_oracle(rng, D, A, clip_eps=0.2, vf_coef=0.5, **kw)
+  N = B * T
+  obs = rng.randn(N, D).astype(f32)
+  action = rng.randn(N, A).astype(f32)
+  old_loc, old_scale = (rng.randn(N, A) * .3).astype(f32), (rng.rand(N, A) * .5 + .5).astype(f32)
+  old_logp = oppo.normal_log_prob(old_loc, old_scale, action)
+  ret, adv = rng.randn(N).astype(f32), rng.randn(N).astype(f32)
+  w = (rng.rand(N) > .2).astype(f32)
+  info, grads = orc.loss_and_grads(obs, action, old_logp, ret, adv, None, w, B, T, old_loc=old_loc,
+                                   old_scale=old_scale)
+  tp = [torch.tensor(p, requires_grad=True) for p in orc.params()]
+  na = len(orc.actor.params())
+
+  def run(params, x):
+    for i in range(0, len(params), 2):
+      x = x @ params[i] + params[i + 1]
+      if i + 2 < len(params):
+        x = torch.tanh(x)
+    return x
+  xo = torch.tensor(obs)
+  loc = 2.0 * torch.tanh(run(tp[:na], xo))
+  scale = torch.nn.functional.softplus(tp[na]).expand_as(loc)
+  v = run(tp[na + 1:], xo)[:, 0]
+  dist = torch.distributions.Normal(loc, scale)
+  logp = dist.log_prob(torch.tensor(action)).sum(-1)
+  ratio = torch.exp(logp - torch.tensor(old_logp))
+  a_t, w_t = torch.tensor(adv), torch.tensor(w)
+  pg = (-torch.minimum(ratio * a_t, torch.clamp(ratio, .8, 1.2) * a_t) * w_t).reshape(B, T).mean(1).sum() / B
+  ve = .5 * (((torch.tensor(ret) - v) ** 2) * w_t).reshape(B, T).mean(1).sum() / B
+  kl = torch.distributions.kl_divergence(
+      torch.distributions.Normal(torch.tensor(old_loc), torch.tensor(old_scale)), dist).sum(-1) * w_t
+  mean_kl = kl.mean()
+  klp = 50.0 * torch.clamp(mean_kl - 2.0 * 0.01, min=0.0) ** 2 + 1.3 * mean_kl
+  total = pg + ve + klp
+  assert klp.item() > 1e-3                      # the penalty is active in this case
+  np.testing.assert_allclose(info['kl'], klp.item(), rtol=2e-5)
+  np.testing.assert_allclose(info['loss'], total.item(), rtol=2e-5)
+  total.backward()
+  for g, p in zip(grads, tp):
+    np.testing.assert_allclose(g, p.grad.numpy(), rtol=2e-4, atol=2e-6)
+
+
+def test_oracle_train_with_kl_and_observation_normalizer():
+  rng = np.random.RandomState(11)
+  B, T, A, D = 6, 7, 2, 4
+  orc = _make_oracle(rng, D, A, num_epochs=3, clip_eps=0.0, kl_cutoff_factor=2.0, kl_cutoff_coef=1000.0,
+                     initial_adaptive_kl_beta=1.0, adaptive_kl_target=0.01, adaptive_kl_tolerance=0.3,
+                     normalize_observations=True, normalize_rewards=True)
+  exp = dict(observation=rng.randn(B, T, D).astype(f32), action=rng.randn(B, T, A).astype(f32),
+             loc=rng.randn(B, T, A).astype(f32) * .1, scale=np.full((B, T, A), .8, f32),
+             reward=rng.rand(B, T).astype(f32), discount=np.ones((B, T), f32),
+             step_type=np.ones((B, T), np.int32), next_step_type=np.ones((B, T), np.int32))
+  infos = orc.train(exp)
+  assert len(infos) == 3 and all(np.isfinite(i['loss']) for i in infos)
+  assert infos[0]['kl'] > 0 and orc.beta != 1.0          # far from the behaviour policy -> beta moved
+  assert orc.obs_normalizer.count[0] > 1 and orc.reward_normalizer.count > 1

@@ -28,7 +28,7 @@ def _ppo_loss(cuda, loc, scale, action, old_logp, adv, ret, v, v_old, w, T, **kw
   d = lambda a: None if a is None else torch.as_tensor(np.ascontiguousarray(a, dtype=f32), device=cuda)
   t = dict(loc=d(loc), scale=d(scale), action=d(action), old=d(old_logp), adv=d(adv), ret=d(ret),
            v=d(v), vo=d(v_old), w=d(w))
-  losses = torch.empty(5, device=cuda)
+  losses = torch.empty(6, device=cuda)
   dloc = torch.empty(N, A, device=cuda); dscale = torch.empty(N, A, device=cuda); dv = torch.empty(N, device=cuda)
   flag = torch.zeros(1, dtype=torch.int32, device=cuda)
   ws, nb = workspace.get(cuda)
@@ -37,7 +37,7 @@ def _ppo_loss(cuda, loc, scale, action, old_logp, adv, ret, v, v_old, w, T, **kw
             _lib.ptr(t['w']), N, A, T, float(kw.get('global_batch', N // T)), kw.get('clip_eps', 0.2),
             kw.get('value_clip', 0.0), kw.get('vf_coef', 0.5), kw.get('ent_coef', 0.0),
             kw.get('logp_clip', 0.0), _lib.ptr(losses), _lib.ptr(dloc), _lib.ptr(dscale), A, _lib.ptr(dv),
-            _lib.ptr(flag), _lib.ptr(ws), nb, _lib.stream())
+            _lib.ptr(flag), None, _lib.ptr(ws), nb, _lib.stream())
   return losses.cpu().numpy(), dloc.cpu().numpy(), dscale.cpu().numpy(), dv.cpu().numpy()
 
 
@@ -232,3 +232,101 @@ def test_ppo_collect_policy(cuda):
   assert not torch.equal(step.action, step2.action)
   greedy = agent.policy.action(ts.restart(obs, batch_size=4096))
   assert torch.equal(greedy.action, loc)
+
+
+# ---- KL penalty (ppo_agent.py:1514-1690) ---------------------------------------------------------
+def _kl_agent(cuda, **kw):
+  from agents_b200.agents.ppo import ppo_agent
+  obs_spec = tensor_spec.TensorSpec((2,), torch.float32, 'observation')
+  act_spec = tensor_spec.BoundedTensorSpec((1,), torch.float32, -1.0, 1.0, 'action')
+  actor = actor_distribution_network.ActorDistributionNetwork(obs_spec, act_spec, fc_layer_params=None,
+                                                              device=cuda).set_seed(1)
+  value = value_network.ValueNetwork(obs_spec, fc_layer_params=None, device=cuda).set_seed(2)
+  agent = ppo_agent.PPOAgent(ts.time_step_spec(obs_spec), act_spec, optimizers.Adam(1e-3), actor_net=actor,
+                             value_net=value, use_gae=True, **kw)
+  agent.initialize()
+  return agent
+
+
+def test_kl_reference_goldens_through_the_agent(cuda):
+  """ppo_agent_test.py:1045-1078 (kl_cutoff_loss = coef * 0.24^2), :1080-1124 (adaptive loss moves
+  with beta), :1126-1164 (beta 1.0 -> 1.0 -> 1.5 -> 1.0)."""
+  kl = torch.tensor([[1.5, -0.5, 6.5, -1.5, -2.3]], device=cuda)
+  for coef in (0.0, 30.0):
+    agent = _kl_agent(cuda, kl_cutoff_factor=5.0, adaptive_kl_target=0.1, kl_cutoff_coef=coef)
+    np.testing.assert_allclose(agent.kl_cutoff_loss(kl).item(), coef * 0.24 ** 2, rtol=1e-5)
+  agent = _kl_agent(cuda, initial_adaptive_kl_beta=1.0, adaptive_kl_target=10.0, adaptive_kl_tolerance=0.5)
+  t = lambda v: torch.tensor([v], device=cuda)
+  assert agent.adaptive_kl_loss(t(10.0)).item() == agent.adaptive_kl_loss(t(10.0)).item()
+  l1 = agent.adaptive_kl_loss(t(1.0)).item()
+  agent.update_adaptive_kl_beta(t(1.0))
+  assert l1 > agent.adaptive_kl_loss(t(1.0)).item()
+  l1 = agent.adaptive_kl_loss(t(100.0)).item()
+  agent.update_adaptive_kl_beta(t(100.0))
+  assert l1 < agent.adaptive_kl_loss(t(100.0)).item()
+  agent = _kl_agent(cuda, initial_adaptive_kl_beta=1.0, adaptive_kl_target=10.0, adaptive_kl_tolerance=0.5)
+  assert agent.update_adaptive_kl_beta(t(10.0)).item() == 1.0
+  assert agent.update_adaptive_kl_beta(t(100.0)).item() == 1.5
+  np.testing.assert_allclose(agent.update_adaptive_kl_beta(t(1.0)).item(), 1.0, rtol=1e-6)
+  # PPOAgent with the reference's default KL settings constructs (it used to raise)
+  _kl_agent(cuda)
+
+
+def test_kl_kernel_parity(cuda):
+  rng = np.random.RandomState(4)
+  N, A = 777, 6
+  la, lb = (rng.randn(N, A) * .4).astype(f32), (rng.randn(N, A) * .4).astype(f32)
+  sa, sb = (rng.rand(N, A) * .5 + .4).astype(f32), (rng.rand(N, A) * .5 + .4).astype(f32)
+  w = (rng.rand(N) > .3).astype(f32)
+  d = lambda a: torch.as_tensor(a, device=cuda)
+  out_kl = torch.empty(N, device=cuda)
+  s = torch.empty(1, device=cuda)
+  ws, nb = workspace.get(cuda)
+  _lib.call('b200rl_ppo_kl', _lib.ptr(d(lb)), _lib.ptr(d(sb)), A, _lib.ptr(d(la)), _lib.ptr(d(sa)), A,
+            _lib.ptr(d(w)), N, A, 1.0 / N, _lib.ptr(out_kl), _lib.ptr(s), _lib.ptr(ws), nb, _lib.stream())
+  want = oppo.normal_kl(la, sa, lb, sb) * w
+  np.testing.assert_allclose(out_kl.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
+  np.testing.assert_allclose(s.item(), want.mean(dtype=f32), rtol=1e-5)
+
+
+@pytest.mark.parametrize('cfg', [
+    dict(kl_cutoff_factor=2.0, kl_cutoff_coef=1000.0, initial_adaptive_kl_beta=1.0, adaptive_kl_target=0.01,
+         adaptive_kl_tolerance=0.3, importance_ratio_clipping=0.0),          # reference defaults (:140-144)
+    dict(kl_cutoff_factor=0.0, kl_cutoff_coef=0.0, initial_adaptive_kl_beta=0.7, adaptive_kl_target=0.05,
+         adaptive_kl_tolerance=0.5, importance_ratio_clipping=0.2),
+])
+def test_ppo_agent_kl_train_parity(cuda, cfg):
+  """PPOAgent (KL-penalty form) with BOTH normalisers on, 3 train calls x 2 epochs vs the oracle:
+  losses, kl_penalty_loss, adaptive beta and parameters."""
+  from agents_b200.agents.ppo import ppo_agent
+  rng = np.random.RandomState(9)
+  B, T, D, A = 64, 33, 17, 6
+  obs_spec = tensor_spec.TensorSpec((D,), torch.float32, 'observation')
+  act_spec = tensor_spec.BoundedTensorSpec((A,), torch.float32, -1.0, 1.0, 'action')
+  actor = actor_distribution_network.ActorDistributionNetwork(obs_spec, act_spec, fc_layer_params=(64, 32),
+                                                              activation_fn='tanh', device=cuda).set_seed(1)
+  value = value_network.ValueNetwork(obs_spec, fc_layer_params=(64, 32), activation_fn='tanh',
+                                     device=cuda).set_seed(2)
+  agent = ppo_agent.PPOAgent(ts.time_step_spec(obs_spec), act_spec, optimizers.Adam(1e-3), actor_net=actor,
+                             value_net=value, use_gae=True, num_epochs=2, normalize_rewards=True,
+                             normalize_observations=True, **cfg)
+  agent.initialize()
+  orc = oppo.PPOOracle(_mirror(actor), actor._std.bias.cpu().numpy().copy(), _mirror(value), -np.ones(A, f32),
+                       np.ones(A, f32), ooptim.AdamTF(1e-3, eps=1e-7), num_epochs=2,
+                       clip_eps=cfg['importance_ratio_clipping'], vf_coef=0.5, gamma=0.99, lam=0.95,
+                       normalize_rewards=True, normalize_observations=True, obs_dim=D,
+                       kl_cutoff_factor=cfg['kl_cutoff_factor'], kl_cutoff_coef=cfg['kl_cutoff_coef'],
+                       initial_adaptive_kl_beta=cfg['initial_adaptive_kl_beta'],
+                       adaptive_kl_target=cfg['adaptive_kl_target'],
+                       adaptive_kl_tolerance=cfg['adaptive_kl_tolerance'])
+  for it in range(3):
+    e = _experience(rng, B, T, D, A)
+    want = orc.train(e)[-1]
+    got = agent.train(_to_traj(cuda, e))
+    np.testing.assert_allclose(got.loss.item(), want['loss'], rtol=2e-5, atol=1e-7)
+    np.testing.assert_allclose(got.extra.kl_penalty_loss.item(), want['kl'], rtol=1e-4, atol=1e-7)
+    np.testing.assert_allclose(got.extra.value_estimation_loss.item(), want['ve'], rtol=2e-5)
+    np.testing.assert_allclose(agent._adaptive_kl_beta.item(), orc.beta, rtol=1e-6)
+  for v, w in zip(actor.variables + value.variables, orc.actor.params() + [orc.std_bias] + orc.value.params()):
+    np.testing.assert_allclose(v.cpu().numpy(), w, rtol=2e-3, atol=2e-5)
+  agent.check_numerics()
