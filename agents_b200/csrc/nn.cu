@@ -60,6 +60,7 @@ struct ARow {
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return p + off; }
 };
 struct ACol {
   const float* p;
@@ -72,30 +73,35 @@ struct ACol {
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return p + off; }
 };
 struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   const float* p;
   int64_t ld;
   static constexpr bool kNContig = true;
   static constexpr bool kKContig = false;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
   __device__ __forceinline__ int64_t row_off(int64_t n) const { return n; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return p + off; }
 };
 struct BCol {  // B(k, n) = p[n*ld + k]  (k contiguous)
   const float* p;
   int64_t ld;
   static constexpr bool kNContig = false;
   static constexpr bool kKContig = true;
+  static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[n * ld + k]; }
   __device__ __forceinline__ int64_t row_off(int64_t n) const { return n * ld; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return p + off; }
 };
 
 struct ConvGeom {
@@ -171,6 +177,7 @@ struct AConv {
   __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
   __device__ __forceinline__ float ld1(int64_t off) const { return v.load_fast(off); }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return v.load4(off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return v.x + off; }
 };
 template <typename T>
 struct AConvT {
@@ -185,6 +192,7 @@ struct AConvT {
   __device__ __forceinline__ bool vec4_ok() const { return v.vec4_ok(); }
   __device__ __forceinline__ float ld1(int64_t off) const { return v.load_fast(off); }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return v.load4(off); }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return v.x + off; }
 };
 
 // Raw uint8 pixel views for the tensor-core path: values 0..255 are exact in TF32, the 1/scale of
@@ -202,6 +210,7 @@ struct AConvU8Raw {
     const uchar4 u = *reinterpret_cast<const uchar4*>(v.x + off);
     return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
   }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return v.x + off; }
 };
 struct AConvTU8Raw {
   ConvView<uint8_t> v;
@@ -216,6 +225,7 @@ struct AConvTU8Raw {
     const uchar4 u = *reinterpret_cast<const uchar4*>(v.x + off);
     return make_float4((float)u.x, (float)u.y, (float)u.z, (float)u.w);
   }
+  __device__ __forceinline__ const void* addr(int64_t off) const { return v.x + off; }
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -240,6 +250,7 @@ __device__ __forceinline__ float dact(float y, float g, int act) {
 
 }  // namespace b200rl
 #include "tc_gemm.cuh"
+#include "tc2_gemm.cuh"
 namespace b200rl {
 
 constexpr int BK = 16;
@@ -569,11 +580,104 @@ static int launch_tc_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::
   return B200RL_OK;
 }
 
+
+// ---- second-generation (persistent, cp.async) kernel: eligibility and launch ---------------------
+// tc2 only takes operands whose every 16-byte chunk is contiguous and aligned in global memory;
+// everything else stays on tc_gemm_kernel (which has the scalar paths).
+static int g_tc2_host_flags = 0;   // bit 1: route everything to the first-generation kernel
+static int tc2_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200RL_TC2");
+    v = e ? atoi(e) : 1;
+  }
+  return v && !(g_tc2_host_flags & 2);
+}
+static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
+static bool tc2_ok(const ARow& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (K & 3) == 0; }
+static bool tc2_ok(const BCol& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (K & 3) == 0; }
+static bool tc2_ok(const ACol& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (rows & 3) == 0; }
+static bool tc2_ok(const BRow& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (rows & 3) == 0; }
+static bool conv_f32_ok(const ConvView<float>& v) {
+  return (v.g.C & 3) == 0 && (v.g.in_img & 3) == 0 && al16(v.x);
+}
+static bool tc2_ok(const AConv<float>& v, int64_t rows, int64_t K) { return conv_f32_ok(v.v); }
+static bool tc2_ok(const AConvT<float>& v, int64_t rows, int64_t K) { return conv_f32_ok(v.v); }
+static bool conv_u8_ok(const ConvView<uint8_t>& v) {
+  const int64_t kwc = (int64_t)v.g.KW * v.g.C;
+  return (kwc & 15) == 0 && (((int64_t)v.g.stride * v.g.C) & 15) == 0 && (v.g.in_row & 15) == 0 &&
+         (v.g.in_img & 15) == 0 && al16(v.x);
+}
+static bool tc2_ok(const AConvU8Raw& v, int64_t rows, int64_t K) { return conv_u8_ok(v.v) && (K & 15) == 0; }
+static bool tc2_ok(const AConvTU8Raw& v, int64_t rows, int64_t K) { return conv_u8_ok(v.v) && (rows & 15) == 0; }
+template <class V>
+static bool tc2_ok(const V&, int64_t, int64_t) { return false; }   // AConv<uint8_t> with the exact division etc.
+
+template <int BN, int PASSES, int EPI, class AL, class BL>
+static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
+  using L = tc2::Layout<BN, PASSES, AL::kExact>;
+  auto kernel = tc2::tc2_gemm_kernel<BN, PASSES, EPI, AL, BL>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kBytes);
+    if (e != cudaSuccess) {
+      set_error("tc2_gemm: cannot set dynamic smem to %d: %s", L::kBytes, cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+    configured = true;
+  }
+  const int64_t tm = (g.M + tc::kBM - 1) / tc::kBM, tn = (g.N + BN - 1) / BN;
+  const int64_t tiles = tm * tn;
+  int splits = 1;
+  const int64_t target = kNumSMs;                  // one persistent CTA per SM
+  if (tiles < target && g.K >= 8 * tc::kBK && (g.ws != nullptr || EPI != tc::EPI_STORE)) {
+    int64_t want = target / tiles;
+    int64_t max_by_k = g.K / (4 * tc::kBK);
+    int64_t max_by_ws = EPI != tc::EPI_STORE ? 65535 : g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t s = want < max_by_k ? want : max_by_k;
+    if (s > max_by_ws) s = max_by_ws;
+    if (s >= 2) splits = (int)s;
+  }
+  int64_t kps = (g.K + splits - 1) / splits;
+  kps = (kps + tc::kBK - 1) / tc::kBK * tc::kBK;
+  splits = (int)((g.K + kps - 1) / kps);
+  if (splits < 1) splits = 1;
+  const int64_t total = tiles * splits;
+  const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
+  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn);
+  B200RL_CHECK_LAUNCH("tc2_gemm");
+  if (splits > 1 && EPI == tc::EPI_STORE) {
+    const int64_t MN = g.M * g.N;
+    B200RL_LAUNCH(splitk_reduce_kernel, (unsigned)((MN + 255) / 256), 256, 0, g.st, (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta, g.mask);
+    B200RL_CHECK_LAUNCH("splitk_reduce");
+  }
+  return B200RL_OK;
+}
+
+// BN by N like the first-generation dispatch
+template <int PASSES, int EPI, class AL, class BL>
+static int launch_tc2(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
+  if (g.N <= 32) return launch_tc2_cfg<32, PASSES, EPI>(a, b, g, epi);
+  if (g.N <= 64) return launch_tc2_cfg<64, PASSES, EPI>(a, b, g, epi);
+  return launch_tc2_cfg<128, PASSES, EPI>(a, b, g, epi);
+}
+template <class V> struct Tc2Capable { static constexpr bool value = true; };
+template <> struct Tc2Capable<AConv<uint8_t>> { static constexpr bool value = false; };
+template <> struct Tc2Capable<AConvT<uint8_t>> { static constexpr bool value = false; };
+template <class AL, class BL>
+static bool use_tc2(const AL& a, const BL& b, const GemmArgs& g) {
+  return tc2_enabled() && tc2_ok(a, g.M, g.K) && tc2_ok(b, g.N, g.K);
+}
+
 template <int PASSES, class AL, class BL>
 static int launch_tc(const AL& a, const BL& b, const GemmArgs& g) {
   tc::EpiArgs none{};
   none.mask = g.mask;
   B200RL_CHECK_ARG(!(g.mask.y && g.beta), "gemm: an input-gradient mask cannot be combined with accumulation");
+  if constexpr (Tc2Capable<AL>::value) {
+    if (use_tc2(a, b, g)) return launch_tc2<PASSES, tc::EPI_STORE>(a, b, g, none);
+  }
   if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), PASSES, tc::EPI_STORE>(a, b, g, none);  // <= 96 KB -> 2 CTAs/SM
   if (g.N <= 64) return launch_tc_cfg<64, 2, PASSES, tc::EPI_STORE>(a, b, g, none);  // 96 KB -> 2 CTAs/SM
   return launch_tc_cfg<128, 3, PASSES, tc::EPI_STORE>(a, b, g, none);
@@ -628,6 +732,12 @@ static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g, float* 
   if (fuse_db) {
     none.colsum = db;
     if (db_fused) *db_fused = true;
+  }
+  if constexpr (Tc2Capable<AL>::value) {
+    if (use_tc2(a, b, g)) {
+      if (mode == 2) return launch_tc2<1, tc::EPI_ATOMIC>(a, b, g, none);
+      return launch_tc2<3, tc::EPI_ATOMIC>(a, b, g, none);
+    }
   }
   if (mode == 2) {
     if (g.N <= 32) return launch_tc_cfg<32, (AL::kExact ? 4 : 2), 1, tc::EPI_ATOMIC>(a, b, g, none);
@@ -693,6 +803,16 @@ int b200rl_tc_debug_variant(int v) {
   cudaError_t e = cudaMemcpyToSymbol(tc::g_tc_variant, &v, sizeof(v));
   if (e != cudaSuccess) {
     set_error("tc_debug_variant: %s", cudaGetErrorString(e));
+    return B200RL_ERR_CUDA;
+  }
+  return B200RL_OK;
+}
+
+int b200rl_set_tc2_flags(int flags) {
+  g_tc2_host_flags = flags;
+  cudaError_t e = cudaMemcpyToSymbol(tc2::g_tc2_flags, &flags, sizeof(flags));
+  if (e != cudaSuccess) {
+    set_error("set_tc2_flags: %s", cudaGetErrorString(e));
     return B200RL_ERR_CUDA;
   }
   return B200RL_OK;
@@ -818,8 +938,13 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     GemmArgs g{nullptr, nullptr, M, K, F, B200RL_ACT_NONE, 0, nullptr, 0, st};
     tc::EpiArgs epi{cg, dX};
     epi.mask = mask;
-    if (gemm_mode() == 2) rc = launch_tc_cfg<128, 3, 1, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
-    else rc = launch_tc_cfg<128, 3, 3, tc::EPI_COL2IM>(ARow{dY, F}, BCol{Wt, F}, g, epi);
+    const ARow da{dY, F};
+    const BCol db_{Wt, F};
+    if (use_tc2(da, db_, g)) {
+      if (gemm_mode() == 2) rc = launch_tc2_cfg<128, 1, tc::EPI_COL2IM>(da, db_, g, epi);
+      else rc = launch_tc2_cfg<128, 3, tc::EPI_COL2IM>(da, db_, g, epi);
+    } else if (gemm_mode() == 2) rc = launch_tc_cfg<128, 3, 1, tc::EPI_COL2IM>(da, db_, g, epi);
+    else rc = launch_tc_cfg<128, 3, 3, tc::EPI_COL2IM>(da, db_, g, epi);
     if (rc) return rc;
   } else if (dX) {  // dcol[M,K] = dY @ W^T, then gather-form col2im
     const int64_t need = M * K * (int64_t)sizeof(float);

@@ -1,0 +1,622 @@
+// Persistent, warp-specialised tcgen05 GEMM (second generation of tc_gemm.cuh).
+//
+//   C[M,N] (+)= act(A[M,K] @ B[K,N] + bias)   over the operand views of nn.cu, 3xTF32 or 1xTF32
+//
+// What changed against tc_gemm.cuh, and why (profiles/r2/README.md, run 1): the first kernel ran
+// ONE output tile per CTA with 8 producer warps that pulled operands through registers
+// (LDG -> split -> STS); ncu showed (a) 80-225 KB of SASS per instantiation, i.e. an instruction
+// cache that never warms, (b) producers stalled on their own loads (long-scoreboard on the first
+// use of every LDG) with ~400 issued instructions per K block per warp for 6 loads, (c) the
+// prologue (TMEM allocation, barrier init) and the epilogue exposed on every tile.  Here:
+//
+//   * one CTA per SM, persistent over (split, m-tile, n-tile) work items;
+//   * warps 0-3   LOADERS: cp.async (LDGSTS, 16 B, zero-fill) of the raw operand chunks straight
+//                 into their final 128B-swizzled position of a deep stage ring; completion is
+//                 signalled with cp.async.mbarrier.arrive.noinc, so the loader never waits for
+//                 data and runs ahead by the full ring;
+//   * warps 4-7   CONVERTERS: shared -> shared; split every fp32 chunk into its TF32 hi plane
+//                 (in place) and lo plane, or expand raw uint8 pixels to fp32; linear,
+//                 conflict-free addressing, no global address arithmetic; they also accumulate
+//                 the fused bias gradient (column sums of B) of weight-gradient GEMMs;
+//   * warp 8      one thread issues tcgen05.mma into one of TWO TMEM accumulators;
+//   * warps 9-12  EPILOGUE of tile i (tcgen05.ld, bias/activation/act' mask, stores, split-K
+//                 red.add, fused col2im scatter-add) overlaps the main loop of tile i+1;
+//   * every loop that is not a fixed 4-8x unroll is rolled, the scalar fall-back paths live in
+//                 tc_gemm.cuh (the host dispatch only sends 16-byte-vectorisable views here).
+//
+// Shared-memory operand layouts, descriptors and the 3xTF32 scheme are those of tc_gemm.cuh.
+#pragma once
+#include "tc_gemm.cuh"
+
+namespace b200rl {
+namespace tc2 {
+
+using tc::EpiArgs;
+using tc::EPI_ATOMIC;
+using tc::EPI_COL2IM;
+using tc::EPI_STORE;
+using tc::kBK;
+using tc::kBM;
+using tc::mbar_arrive;
+using tc::mbar_init;
+using tc::mbar_wait;
+using tc::smem_addr;
+
+constexpr int kLoaderThreads = 128;
+constexpr int kConvThreads = 128;
+constexpr int kMmaWarp = 8;
+constexpr int kFirstEpiWarp = 9;
+constexpr int kThreads = 13 * 32;
+
+// The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32 tile IS the
+// hi plane and only the lo plane is computed (x - (x & 0xFFFFE000)); measured bit-identical to
+// the explicitly masked hi plane on every layer (profiles/r2/run2_tc2_check*.jsonl).
+// bit 0 of the flags: store the masked hi plane anyway (A/B switch for tests/profiles).
+__device__ int g_tc2_flags = 0;
+
+template <int BN, int PASSES, bool A_EXACT>
+struct Layout {
+  static constexpr int kATile = kBM * 128;
+  static constexpr int kBTile = BN * 128;
+  static constexpr int kNumA = (PASSES == 3 && !A_EXACT) ? 2 : 1;
+  static constexpr int kNumB = PASSES == 3 ? 2 : 1;
+  static constexpr int kRawA = A_EXACT ? kBM * kBK : 0;   // uint8 staging, expanded into plane A
+  static constexpr int kStage = kNumA * kATile + kNumB * kBTile + kRawA;
+  static constexpr int kBudget = 196 * 1024;
+  static constexpr int kStages = (kBudget / kStage) > 8 ? 8 : (kBudget / kStage);
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + kBarBytes + BN * 4;
+  static_assert(kStage % 1024 == 0, "stage planes must stay 1024 B aligned");
+  static_assert(kStages >= 2, "at least two stages");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+// one out-of-line body instead of 16 inlined tanhf expansions per epilogue step
+__device__ __noinline__ float act_tanh(float x) { return tanhf(x); }
+__device__ __forceinline__ float tf32_hi(float x) {
+  return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+}
+
+struct Work {
+  int64_t m0, n0, kb, ke;
+  int split, nkb;
+  bool first_m;
+};
+__device__ __forceinline__ Work decode_work(int64_t w, int64_t tiles_m, int64_t tiles_n, int BN,
+                                            int64_t K, int64_t k_per_split) {
+  Work o;
+  const int64_t tiles_mn = tiles_m * tiles_n;
+  const int64_t split = w / tiles_mn, rem = w - split * tiles_mn;
+  const int64_t tm = rem / tiles_n, tn = rem - tm * tiles_n;   // n fastest: neighbours share A rows
+  o.split = (int)split;
+  o.m0 = tm * kBM;
+  o.n0 = tn * BN;
+  o.kb = split * k_per_split;
+  o.ke = (o.kb + k_per_split < K) ? o.kb + k_per_split : K;
+  o.nkb = (int)((o.ke - o.kb + kBK - 1) / kBK);
+  o.first_m = tm == 0;
+  return o;
+}
+
+// ---- loaders ------------------------------------------------------------------------------------
+// K-contiguous fp32 view, ROWS x 32 tile: thread t owns chunk j = t & 7 (4 consecutive k) of rows
+// (t >> 3) + 16 i.  sw128(r0 + 16 i, j) = sw128(r0, j) + 2048 i.
+template <int ROWS, class V>
+struct LoadKContigF32 {
+  static constexpr int NR = ROWS / 16;
+  int64_t roff[NR];
+  uint32_t ok, dst0;
+  int j;
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+    j = t & 7;
+    const int r0 = t >> 3;
+    dst0 = tc::sw128((uint32_t)r0, (uint32_t)j);
+    ok = 0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const int64_t r = row0 + r0 + 16 * i;
+      const bool in = r < row_limit;
+      roff[i] = in ? v.row_off(r) : 0;
+      ok |= (in ? 1u : 0u) << i;
+    }
+  }
+  __device__ __forceinline__ void issue(const V& v, uint32_t plane, int64_t k0, int64_t ke) {
+    const int64_t k = k0 + 4 * j;
+    const bool kin = k < ke;                       // K % 4 == 0: a chunk is all in or all out
+    const int64_t koff = kin ? v.k_off(k) : 0;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+      const bool in = kin && ((ok >> i) & 1u);
+      cp_async16(plane + dst0 + 2048u * i, v.addr(in ? roff[i] + koff : 0), in ? 16u : 0u);
+    }
+  }
+};
+
+// MN-major fp32 view (the M/N index is contiguous in memory), 32 x ROWS tile: thread t owns row
+// chunk cm = t % CPR (rows 4cm..4cm+3) at k-rows t / CPR + KSTEP i.  k_off(k) of the conv
+// filter-gradient view is a full (n, oy, ox) decode: lane l computes it for k0 + l once and the
+// offsets are fetched by shuffle.
+template <int ROWS, class V>
+struct LoadMnF32 {
+  static constexpr int CPR = ROWS / 4;
+  static constexpr int KSTEP = kLoaderThreads / CPR;
+  static constexpr int NC = 32 / KSTEP;            // chunks per thread
+  int64_t roff;
+  bool ok;
+  int cm, kk0;
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+    cm = t % CPR;
+    kk0 = t / CPR;
+    const int64_t r = row0 + 4 * cm;
+    ok = r < row_limit;                            // rows % 4 == 0 (host check)
+    roff = ok ? v.row_off(r) : 0;
+  }
+  __device__ __forceinline__ void issue(const V& v, uint32_t plane, int64_t k0, int64_t ke) {
+    const int lane = threadIdx.x & 31;
+    const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int kk = kk0 + KSTEP * i;
+      const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
+      const bool in = ok && (k0 + kk < ke);
+      cp_async16(plane + tc::mn128<ROWS>((uint32_t)cm, (uint32_t)kk),
+                 v.addr(in ? roff + koff : 0), in ? 16u : 0u);
+    }
+  }
+};
+
+// K-contiguous uint8 im2col view (conv1 forward): raw tile [128 rows][32 B]; thread t copies the
+// two 16-byte halves of row t (one ky row of the patch = 32 contiguous bytes).  The halves of rows
+// with bit 2 set are swapped so that the converter's 16-byte reads are bank-conflict free.
+template <class V>
+struct LoadKContigU8 {
+  int64_t roff;
+  bool ok;
+  uint32_t dst[2];
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+    const int64_t r = row0 + t;
+    ok = r < row_limit;
+    roff = ok ? v.row_off(r) : 0;
+    const uint32_t sw = (uint32_t)(t >> 2) & 1u;
+    dst[0] = (uint32_t)t * 32u + ((0u ^ sw) << 4);
+    dst[1] = (uint32_t)t * 32u + ((1u ^ sw) << 4);
+  }
+  __device__ __forceinline__ void issue(const V& v, uint32_t raw, int64_t k0, int64_t ke) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int64_t k = k0 + 16 * h;
+      const bool in = ok && k < ke;                // K % 16 == 0 (host check)
+      cp_async16(raw + dst[h], v.addr(in ? roff + v.k_off(k) : 0), in ? 16u : 0u);
+    }
+  }
+};
+
+// MN-major uint8 view (conv1 filter gradient): raw tile [32 k][128 B]; the 128 patch indices of a
+// k-row are 128/(KW*C) ky segments of contiguous bytes; thread t copies 16-byte chunk c = t & 7 of
+// k-rows (t >> 3) and (t >> 3) + 16.
+template <class V>
+struct LoadMnU8 {
+  int64_t roff;
+  bool ok;
+  int c, kk0;
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+    c = t & 7;
+    kk0 = t >> 3;
+    const int64_t r = row0 + 16 * c;
+    ok = r < row_limit;                            // rows % 16 == 0 (host check)
+    roff = ok ? v.row_off(r) : 0;
+  }
+  __device__ __forceinline__ void issue(const V& v, uint32_t raw, int64_t k0, int64_t ke) {
+    const int lane = threadIdx.x & 31;
+    const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int kk = kk0 + 16 * i;
+      const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
+      const bool in = ok && (k0 + kk < ke);
+      cp_async16(raw + (uint32_t)kk * 128u + (uint32_t)c * 16u, v.addr(in ? roff + koff : 0),
+                 in ? 16u : 0u);
+    }
+  }
+};
+
+template <int ROWS, class V, bool KCONTIG = V::kKContig, bool EXACT = V::kExact>
+struct LoaderFor;
+template <int ROWS, class V>
+struct LoaderFor<ROWS, V, true, false> { using type = LoadKContigF32<ROWS, V>; };
+template <int ROWS, class V>
+struct LoaderFor<ROWS, V, false, false> { using type = LoadMnF32<ROWS, V>; };
+template <int ROWS, class V>
+struct LoaderFor<ROWS, V, true, true> { using type = LoadKContigU8<V>; };
+template <int ROWS, class V>
+struct LoaderFor<ROWS, V, false, true> { using type = LoadMnU8<V>; };
+
+// ---- converters ---------------------------------------------------------------------------------
+// fp32 plane of `bytes` bytes: hi in place, lo at +lo_off; 128 threads, 16 B per thread per step.
+template <bool WITH_LO>
+__device__ __forceinline__ void convert_f32(uint32_t plane, uint32_t lo_off, int bytes, int t,
+                                            bool raw_hi, float4& colsum, bool do_colsum) {
+#pragma unroll 4
+  for (int off = t * 16; off < bytes; off += kConvThreads * 16) {
+    const float4 v = lds128(plane + off);
+    float4 h;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    if (!raw_hi) sts128(plane + off, h);
+    if (WITH_LO) sts128(plane + lo_off + off, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+    if (do_colsum) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
+  }
+}
+__device__ __forceinline__ void u8x4_to_f32(uint32_t w, float4& o) {
+  o.x = (float)(w & 0xFFu);
+  o.y = (float)((w >> 8) & 0xFFu);
+  o.z = (float)((w >> 16) & 0xFFu);
+  o.w = (float)(w >> 24);
+}
+// raw [128 rows][32 B] uint8 -> K-major SWIZZLE_128B fp32 tile: thread t expands row t
+__device__ __forceinline__ void convert_u8_kcontig(uint32_t raw, uint32_t plane, int t) {
+  const uint32_t sw = (uint32_t)(t >> 2) & 1u;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    uint4 p;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
+                 : "r"(raw + (uint32_t)t * 32u + (((uint32_t)h ^ sw) << 4))
+                 : "memory");
+    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      u8x4_to_f32(w[q], o);
+      sts128(plane + tc::sw128((uint32_t)t, (uint32_t)(4 * h + q)), o);
+    }
+  }
+}
+// raw [32 k][128 B] uint8 -> MN-major fp32 tile (128 rows): thread t expands 16-byte chunk c = t & 7
+// of k-rows (t >> 3) and (t >> 3) + 16, i.e. row chunks 4c..4c+3
+__device__ __forceinline__ void convert_u8_mn(uint32_t raw, uint32_t plane, int t) {
+  const int c = t & 7;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int kk = (t >> 3) + 16 * i;
+    uint4 p;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
+                 : "r"(raw + (uint32_t)kk * 128u + (uint32_t)c * 16u)
+                 : "memory");
+    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float4 o;
+      u8x4_to_f32(w[q], o);
+      sts128(plane + tc::mn128<kBM>((uint32_t)(4 * c + q), (uint32_t)kk), o);
+    }
+  }
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int BN, int PASSES, int EPI, class AL, class BL>
+__global__ void __launch_bounds__(kThreads, 1)
+    tc2_gemm_kernel(const AL a, const BL b, const EpiArgs epi, float* __restrict__ C,
+                    const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int act,
+                    int beta, int splits, int64_t k_per_split, float* __restrict__ ws,
+                    float out_scale, int64_t tiles_m, int64_t tiles_n) {
+  using L = Layout<BN, PASSES, AL::kExact>;
+  constexpr int S = L::kStages;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t smem_base = smem_addr(smem);
+  unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + S * L::kStage);
+  unsigned long long* raw_full = bars;            // loaders' cp.async landed
+  unsigned long long* conv_full = bars + S;       // converters done -> MMA may read
+  unsigned long long* empty = bars + 2 * S;       // MMAs of the stage retired -> loaders
+  unsigned long long* acc_full = bars + 3 * S;    // [2] accumulator complete -> epilogue
+  unsigned long long* acc_empty = acc_full + 2;   // [2] epilogue drained it -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* scol = reinterpret_cast<float*>(smem + S * L::kStage + L::kBarBytes);   // [BN] column sums
+  static_assert((3 * 8 + 4) * 8 + 8 <= L::kBarBytes, "barrier block too small");
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  pdl_launch_dependents();
+  if (tid == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(smem_addr(&raw_full[s]), kLoaderThreads);
+      mbar_init(smem_addr(&conv_full[s]), kConvThreads / 32);
+      mbar_init(smem_addr(&empty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_addr(&acc_full[i]), 1);
+      mbar_init(smem_addr(&acc_empty[i]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid < BN) scol[tid] = 0.f;
+  constexpr int kCols = 2 * BN;                    // two accumulators; power of two >= 64
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_addr(tmem_slot)),
+                 "n"(kCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                      // nothing above touched global memory
+
+  const int64_t total = tiles_m * tiles_n * (int64_t)splits;
+  constexpr bool kLoA = PASSES == 3 && !AL::kExact;
+  constexpr bool kLoB = PASSES == 3;
+  constexpr uint32_t kOffB = L::kNumA * L::kATile;
+  constexpr uint32_t kOffRaw = kOffB + L::kNumB * L::kBTile;
+
+  if (warp < 4) {
+    // ======================= loaders =======================
+    typename LoaderFor<kBM, AL>::type la;
+    typename LoaderFor<BN, BL>::type lb;
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      la.begin_tile(a, wk.m0, M, tid);
+      lb.begin_tile(b, wk.n0, N, tid);
+#pragma unroll 1
+      for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1u;
+        mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
+        const uint32_t st = smem_base + s * L::kStage;
+        const int64_t k0 = wk.kb + (int64_t)kbi * kBK;
+        la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
+        lb.issue(b, st + kOffB, k0, wk.ke);
+        cp_async_arrive(smem_addr(&raw_full[s]));
+      }
+    }
+  } else if (warp < 8) {
+    // ======================= converters =======================
+    const int t = tid - kLoaderThreads;
+    const bool raw_hi = (g_tc2_flags & 1) == 0;
+    uint32_t it = 0;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      const bool do_colsum = EPI == EPI_ATOMIC && !BL::kKContig && epi.colsum != nullptr && wk.first_m;
+      float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+      for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1u;
+        mbar_wait(smem_addr(&raw_full[s]), ph);
+        const uint32_t st = smem_base + s * L::kStage;
+        float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (AL::kExact) {
+          if (AL::kKContig) convert_u8_kcontig(st + kOffRaw, st, t);
+          else convert_u8_mn(st + kOffRaw, st, t);
+        } else if (PASSES == 3 || !raw_hi) {
+          convert_f32<kLoA>(st, L::kATile, L::kATile, t, raw_hi, none, false);
+        }
+        if (PASSES == 3 || !raw_hi || do_colsum)
+          convert_f32<kLoB>(st + kOffB, L::kBTile, L::kBTile, t, raw_hi, csum, do_colsum);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_addr(&conv_full[s]));
+      }
+      if (do_colsum) {
+        // Every chunk of a thread covers the same 4 columns (the MN-major atom layout repeats
+        // with the thread stride): decode them from the thread's first byte offset.
+        const uint32_t off = (uint32_t)t * 16u, within = off & 511u;
+        const uint32_t kin = within >> 7, blk = (within & 127u) >> 4;
+        const uint32_t c = (((blk >> 1) ^ kin) << 1) | (blk & 1u);
+        const uint32_t cm = ((off >> 9) % (BN / 32)) * 8u + c;
+        atomicAdd(&scol[4 * cm + 0], csum.x);
+        atomicAdd(&scol[4 * cm + 1], csum.y);
+        atomicAdd(&scol[4 * cm + 2], csum.z);
+        atomicAdd(&scol[4 * cm + 3], csum.w);
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        if (t < BN) {
+          const float v = scol[t];
+          scol[t] = 0.f;
+          if (wk.n0 + t < N) atomicAdd(epi.colsum + wk.n0 + t, v);
+        }
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ======================= MMA issuer =======================
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc(BN, !AL::kKContig, !BL::kKContig);
+      uint32_t it = 0, tl = 0;
+      for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+        const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+        const uint32_t buf = tl & 1u;
+        mbar_wait(smem_addr(&acc_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t tmem_d = tmem_base + buf * BN;
+#pragma unroll 1
+        for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1u;
+          mbar_wait(smem_addr(&conv_full[s]), ph);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_hi = smem_base + s * L::kStage, a_lo = a_hi + L::kATile;
+          const uint32_t b_hi = a_hi + kOffB, b_lo = b_hi + L::kBTile;
+#pragma unroll
+          for (int ks = 0; ks < kBK / 8; ++ks) {
+            const uint32_t ka = AL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (kBM / 32) * 512u;
+            const uint32_t kbo = BL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (BN / 32) * 512u;
+            auto da = [&](uint32_t base) {
+              return AL::kKContig ? tc::make_desc(base + ka) : tc::make_desc_mn(base + ka, (kBM / 32) * 512u);
+            };
+            auto db = [&](uint32_t base) {
+              return BL::kKContig ? tc::make_desc(base + kbo) : tc::make_desc_mn(base + kbo, (BN / 32) * 512u);
+            };
+            const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
+            if (PASSES == 3 && AL::kExact) {
+              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_lo), idesc, first);
+              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, 1u);
+            } else if (PASSES == 3) {
+              tc::tc_mma_tf32(tmem_d, da(a_lo), db(b_hi), idesc, first);
+              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_lo), idesc, 1u);
+              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, 1u);
+            } else {
+              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, first);
+            }
+          }
+          tc::tc_commit(smem_addr(&empty[s]));
+        }
+        tc::tc_commit(smem_addr(&acc_full[buf]));
+      }
+    }
+    __syncwarp();
+  } else {
+    // ======================= epilogue =======================
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    uint32_t tl = 0;
+    for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      const uint32_t buf = tl & 1u;
+      mbar_wait(smem_addr(&acc_full[buf]), (tl >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int64_t m = wk.m0 + q * 32 + lane;
+      float* out = (splits > 1 && EPI == EPI_STORE) ? ws + (int64_t)wk.split * M * N : C;
+      const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
+      const bool final_pass = splits == 1;
+      // col2im destination of this row (EPI_COL2IM): pos -> (n, oy, ox)
+      float* cbase = nullptr;
+      const float* ybase = nullptr;
+      int64_t wc = 0;
+      if (EPI == EPI_COL2IM && m < M) {
+        uint32_t img, rem, oy, ox;
+        epi.g.d_ohow.divmod((uint32_t)m, img, rem);
+        epi.g.d_ow.divmod(rem, oy, ox);
+        wc = (int64_t)epi.g.W * epi.g.C;
+        const int64_t in_off = (int64_t)oy * epi.g.stride * wc + (int64_t)ox * epi.g.stride * epi.g.C;
+        cbase = epi.dx + (int64_t)img * epi.g.H * wc + in_off;
+        if (epi.mask.y) ybase = epi.mask.y + (int64_t)img * epi.mask.ld + in_off;
+      }
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 16) {
+        uint32_t r[16];
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+              "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int64_t nb = wk.n0 + c;
+        if (m >= M || nb >= N) continue;
+        if (EPI == EPI_COL2IM) {
+          float4 y4[4];
+          uint32_t off4[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {            // 4-channel groups: patch index -> (ky, kx*C + c)
+            uint32_t ky, rr;
+            epi.g.d_kwc.divmod((uint32_t)(nb + 4 * j), ky, rr);
+            off4[j] = (uint32_t)(ky * wc + rr);
+            if (ybase && nb + 4 * j < N) y4[j] = *reinterpret_cast<const float4*>(ybase + off4[j]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            if (nb + 4 * j >= N) break;
+            float4 v = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            if (ybase) {
+              v.x = dact(y4[j].x, v.x, epi.mask.act); v.y = dact(y4[j].y, v.y, epi.mask.act);
+              v.z = dact(y4[j].z, v.z, epi.mask.act); v.w = dact(y4[j].w, v.w, epi.mask.act);
+            }
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + off4[j]),
+                         "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                         : "memory");
+          }
+        } else if (EPI == EPI_ATOMIC) {
+          float* dst = C + m * N + nb;
+          if ((N & 3) == 0) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              if (nb + j >= N) break;
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + j),
+                           "f"(__uint_as_float(r[j]) * out_scale),
+                           "f"(__uint_as_float(r[j + 1]) * out_scale),
+                           "f"(__uint_as_float(r[j + 2]) * out_scale),
+                           "f"(__uint_as_float(r[j + 3]) * out_scale)
+                           : "memory");
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < N) atomicAdd(dst + j, __uint_as_float(r[j]) * out_scale);
+          }
+        } else {
+          float v[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
+          if (final_pass) {
+            const bool full = nb + 15 < N;
+            if (bias) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += (full || nb + j < N) ? __ldg(bias + nb + j) : 0.f;
+            }
+            if (act == B200RL_ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            } else if (act == B200RL_ACT_TANH) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = act_tanh(v[j]);
+            }
+            if (epi.mask.y) {
+              const float* yp = epi.mask.y + m * epi.mask.ld + nb;
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full || nb + j < N) v[j] = dact(yp[j], v[j], epi.mask.act);
+            }
+            if (beta) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full || nb + j < N) v[j] += out[m * N + nb + j];
+            }
+          }
+          float* dst = out + m * N + nb;
+          if (vec_out) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              if (nb + j < N)
+                *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (nb + j < N) dst[j] = v[j];
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_addr(&acc_empty[buf]));
+    }
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "n"(kCols));
+  }
+}
+
+}  // namespace tc2
+}  // namespace b200rl

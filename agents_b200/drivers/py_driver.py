@@ -40,30 +40,45 @@ class PyDriver(driver.Driver):
   def info_observers(self):
     return self._info_observers
 
+  def _transition(self, time_step, policy_state):
+    """One interaction: (time_step, policy_state) -> (transition, next policy_state).  The
+    PolicyStep handed to observers carries the state the policy was CALLED with, as the
+    reference's driver does, so recurrent policies can be re-run from stored data."""
+    step = self.policy.action(time_step, policy_state)
+    next_time_step = self.env.step(step.action)
+    return (time_step, step._replace(state=policy_state), next_time_step), step.state
+
+  def _notify(self, transition):
+    traj = trajectory.from_transition(*transition)
+    for obs in self._transition_observers:
+      obs(transition)
+    for obs in self.observers:
+      obs(traj)
+    if self.info_observers:
+      info = self.env.get_info()
+      for obs in self.info_observers:
+        obs(info)
+    return traj
+
   def run(self, time_step, policy_state=()):
-    """Runs the policy from `time_step` / `policy_state`; returns the final pair."""
-    num_steps = 0
-    num_episodes = 0
-    while num_steps < self._max_steps and num_episodes < self._max_episodes:
-      if not self.env.batched and np.all(time_step.is_first()) and num_episodes > 0:
+    """Steps the environment with the policy until `max_steps` non-boundary steps or
+    `max_episodes` episode ends have been seen (whichever budget is finite); returns the final
+    `(time_step, policy_state)` (reference drivers/py_driver.py:100-146)."""
+    steps_left, episodes_left = self._max_steps, self._max_episodes
+    episodes_seen = 0
+    while steps_left > 0 and episodes_left > 0:
+      # an unbatched environment that auto-reset gets a fresh policy state for the new episode
+      if episodes_seen and not self.env.batched and np.all(time_step.is_first()):
         policy_state = self._policy.get_initial_state(self.env.batch_size or 1)
-      action_step = self.policy.action(time_step, policy_state)
-      next_time_step = self.env.step(action_step.action)
-      action_step_with_previous_state = action_step._replace(state=policy_state)
-      traj = trajectory.from_transition(time_step, action_step_with_previous_state, next_time_step)
-      for observer in self._transition_observers:
-        observer((time_step, action_step_with_previous_state, next_time_step))
-      for observer in self.observers:
-        observer(traj)
-      for observer in self.info_observers:
-        observer(self.env.get_info())
-      if self._end_episode_on_boundary:
-        num_episodes += np.sum(traj.is_boundary())
-      else:
-        num_episodes += np.sum(traj.is_last())
-      num_steps += np.sum(~np.asarray(traj.is_boundary()))
-      time_step = next_time_step
-      policy_state = action_step.state
+      transition, policy_state = self._transition(time_step, policy_state)
+      traj = self._notify(transition)
+      boundary = np.asarray(traj.is_boundary())
+      ended = boundary if self._end_episode_on_boundary else np.asarray(traj.is_last())
+      n_ended = int(np.sum(ended))
+      episodes_seen += n_ended
+      episodes_left -= n_ended
+      steps_left -= int(boundary.size - np.sum(boundary))
+      time_step = transition[2]
     return time_step, policy_state
 
 

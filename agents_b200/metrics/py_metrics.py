@@ -16,47 +16,58 @@ from agents_b200.utils import nest
 
 
 class NumpyDeque(object):
-  """Ring of the last `maxlen` values (py_metrics.py:34-91); `maxlen=np.inf` grows unbounded."""
+  """The newest `maxlen` values of a stream, for windowed means.
+
+  Storage is a flat numpy array used as a circular window: `_count` values are valid and the
+  newest sits just before `_next`.  An unbounded deque (`maxlen=np.inf`) never wraps; its array
+  doubles when full.  (Role of py_metrics.NumpyDeque in the reference; the metrics below only
+  need add / extend / clear / len / mean / last.)
+  """
 
   def __init__(self, maxlen, dtype):
-    self._start_index = np.int64(0)
-    self._len = np.int64(0)
-    self._maxlen = np.array(maxlen)
-    initial_len = 10 if np.isinf(self._maxlen) else int(self._maxlen)
-    self._buffer = np.zeros(shape=(initial_len,), dtype=dtype)
+    self._bounded = not np.isinf(maxlen)
+    self._capacity = int(maxlen) if self._bounded else 16
+    if self._capacity < 1:
+      raise ValueError('maxlen must be >= 1.')
+    self._store = np.zeros(self._capacity, dtype=dtype)
+    self._count = 0          # valid entries
+    self._next = 0           # where the next value goes
 
   def clear(self):
-    self._start_index = np.int64(0)
-    self._len = np.int64(0)
+    self._count = 0
+    self._next = 0
+
+  def _grow(self):
+    bigger = np.zeros(2 * self._capacity, dtype=self._store.dtype)
+    bigger[:self._capacity] = self._store
+    self._store, self._capacity = bigger, 2 * self._capacity
 
   def add(self, value):
-    insert_idx = int((self._start_index + self._len) % self._maxlen)
-    if np.isinf(self._maxlen) and insert_idx >= self._buffer.shape[0]:
-      self._buffer.resize((self._buffer.shape[0] * 2,), refcheck=False)
-    self._buffer[insert_idx] = value
-    if self._len < self._maxlen:
-      self._len += 1
-    else:
-      self._start_index = np.mod(self._start_index + 1, self._maxlen)
+    if not self._bounded and self._next == self._capacity:
+      self._grow()
+    self._store[self._next] = value
+    self._next += 1
+    if self._bounded and self._next == self._capacity:
+      self._next = 0
+    self._count = min(self._count + 1, self._capacity) if self._bounded else self._count + 1
 
   def extend(self, values):
-    for value in values:
-      self.add(value)
+    for v in np.asarray(values).reshape(-1):
+      self.add(v)
 
   @property
   def last(self):
-    if self._len == 0:
+    if self._count == 0:
       return None
-    return self._buffer[int((self._start_index + self._len - 1) % self._maxlen)]
+    return self._store[(self._next - 1) % self._capacity]
 
   def __len__(self):
-    return int(self._len)
+    return self._count
 
   def mean(self, dtype=None):
-    if self._len == self._buffer.shape[0]:
-      return np.mean(self._buffer, dtype=dtype)
-    assert self._start_index == 0
-    return np.mean(self._buffer[:self._len], dtype=dtype)
+    # a full bounded window uses the whole array; otherwise the valid part is the prefix
+    window = self._store if self._count == self._capacity else self._store[:self._count]
+    return np.mean(window, dtype=dtype)
 
 
 def _batched(trajectory):
@@ -91,16 +102,20 @@ class PyMetric(abc.ABC):
 
 
 class StreamingMetric(PyMetric):
-  """Average of the metric over the last (up to) `buffer_size` episodes."""
+  """A per-episode quantity averaged over the most recent `buffer_size` finished episodes.
+
+  Subclasses keep one accumulator per environment (`_reset(batch_size)` allocates them,
+  `_batched_call(trajectory)` advances them and calls `add_to_buffer` when episodes end); the
+  accumulators are sized lazily from the first trajectory unless `batch_size` is given."""
 
   def __init__(self, name='StreamingMetric', buffer_size=10, batch_size=None):
     super(StreamingMetric, self).__init__(name)
-    self._buffer = NumpyDeque(maxlen=buffer_size, dtype=np.float64)
+    self._window = NumpyDeque(maxlen=buffer_size, dtype=np.float64)
     self._batch_size = batch_size
     self.reset()
 
   def reset(self):
-    self._buffer.clear()
+    self._window.clear()
     if self._batch_size:
       self._reset(self._batch_size)
 
@@ -109,16 +124,16 @@ class StreamingMetric(PyMetric):
     pass
 
   def add_to_buffer(self, values):
-    self._buffer.extend(values)
+    self._window.extend(values)
 
   @property
   def data(self):
-    return self._buffer
+    return self._window
 
   def result(self):
-    if len(self._buffer):
-      return self._buffer.mean(dtype=np.float32)
-    return np.array(0.0, dtype=np.float32)
+    if len(self._window) == 0:
+      return np.array(0.0, dtype=np.float32)
+    return self._window.mean(dtype=np.float32)
 
   @abc.abstractmethod
   def _batched_call(self, trajectory):

@@ -25,6 +25,7 @@ from agents_b200 import _lib
 from agents_b200.replay_buffers import replay_buffer
 from agents_b200.replay_buffers import table
 from agents_b200.specs import tensor_spec
+from agents_b200.utils import common
 from agents_b200.utils import nest
 
 BufferInfo = collections.namedtuple('BufferInfo', ['ids', 'probabilities'])
@@ -185,6 +186,9 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
     """Tells the host mirror that `n` add_batch launches ran outside this object's view."""
     self._last_id_host += int(n)
 
+  def _note_clear(self):
+    self._last_id_host = -1
+
   def _num_frames(self):
     total = (self._get_last_id() + 1) * self._batch_size
     return torch.tensor(min(total, self._capacity), dtype=torch.int64)
@@ -222,6 +226,9 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
         self._data_table.write(rows, nest.pack_sequence_as(self._data_spec, flat))
         self._last_id.fill_(id_)
     self._last_id_host += 1
+    # inside a captured step (common.function) every replay advances the device counter: keep the
+    # host mirror in step (gather_all / num_frames / the empty check read it)
+    common.record_host_effect(lambda: self._note_adds(1))
 
   # ---- sample ---------------------------------------------------------------------------
   def _get_next(self, sample_batch_size=None, num_steps=None, time_stacked=True, ids=None,
@@ -418,6 +425,7 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
           for v in self._data_table.variables() + self._id_table.variables():
             v.zero_()
     self._last_id_host = -1
+    common.record_host_effect(self._note_clear)
 
   def clear(self, clear_all_variables=False):
     return self._clear(clear_all_variables)

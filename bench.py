@@ -6,13 +6,22 @@ Mnih'15 Q-network, Huber loss, centered RMSProp (examples/dqn/mnih15 config), ga
 target update every 2500 steps.  One "step" = get_next(256, 2) + DqnAgent.train(experience).
 
   value        steps/s with the ring resident in HBM; the step is replayed as ONE CUDA graph.
+               `--steps K` steps are timed `--repeats R` times (each block bracketed by
+               barrier + synchronize, CUDA events, max over ranks); value is the MEDIAN block.
   e2e          the same step through the public API with HOST buffers: every step copies one
                driver step of collected frames (256 x 28 244 B) from pinned host memory,
-               add_batch, get_next, train, and reads the loss back.
-  roofline     the update's GEMM/conv work (the dominant share of the step) against the measured
-               tensor peak; roofline_gather: the replay gather kernel against measured HBM GB/s.
-  cpu_baseline the torch-CPU restatement of the reference train step (oracle/dqn_torch.py) on
-               the host cores (TensorFlow is not installable here).
+               add_batch, get_next, train, and reads that step's loss back (the read of step
+               i-1 overlaps step i: pinned 4-byte slots + events).
+  parity       before timing, 3 train steps on the sampled batches are replayed by the CPU
+               restatement (oracle/dqn_torch.py, same initial weights) and the losses compared.
+  roofline     the update's GEMM/conv work against the measured tensor peak; roofline_gather:
+               the replay gather kernel against measured HBM GB/s.
+  cpu_baseline the torch-CPU restatement of the reference train step on the host cores
+               (TensorFlow is not installable here): 1 M-slot host ring when RAM
+               allows, physical-core thread count, median of 3 blocks.
+  ppo_update / sac_step / cartpole_iter / gather_sweep   BASELINE configs 3 / 4 / 1 / 5
+               (profiles/configs.py); under torchrun they are sharded over the ranks.
+  dp_parity    (N > 1) N replicas on shards vs one replica on the whole batch.
 
 `--impl reference` times that CPU restatement alone (the reference arm of the contract).
 N>1 (torchrun): one process per GPU, each with its own 1M-slot ring shard and a local batch of
@@ -75,53 +84,94 @@ def _mnih_layers(rng):
   return layers
 
 
-def cpu_reference_steps(steps, warmup, seed=0):
-  """Times the CPU restatement: sample (numpy ring gather) + train (torch CPU).  Returns
-  (steps_per_s, cores, sample_description)."""
-  import torch
-  from oracle import dqn_torch
-  from oracle import replay as oreplay
-  cores = os.cpu_count() or 1
-  rng = np.random.RandomState(seed)
-  b_env, l = 64, 256                          # 16 384-slot ring (0.46 GB) on the host
-  shapes = [(), (84, 84, 4), (), (), (), ()]
-  dtypes = [np.int32, np.uint8, np.int32, np.int32, np.float32, np.float32]
-  ring = oreplay.UniformReplayOracle(shapes, dtypes, b_env, l, seed=seed)
-  ring.storage[1][...] = rng.randint(0, 256, size=ring.storage[1].shape, dtype=np.uint8)
-  ring.storage[0][...] = rng.randint(0, 3, size=ring.capacity)
-  ring.storage[2][...] = rng.randint(0, A, size=ring.capacity)
-  ring.storage[4][...] = rng.rand(ring.capacity)
-  ring.storage[5][...] = (rng.rand(ring.capacity) > 0.1)
-  ring.last_id = 2 * l + 17
-  agent = dqn_torch.DqnTorchOracle(_mnih_layers(rng))
+def _physical_cores():
+  """Distinct (physical id, core id) pairs of /proc/cpuinfo; falls back to half the logical CPUs."""
+  try:
+    pairs, phys = set(), None
+    for line in open('/proc/cpuinfo'):
+      if line.startswith('physical id'):
+        phys = line.split(':')[1].strip()
+      elif line.startswith('core id'):
+        pairs.add((phys, line.split(':')[1].strip()))
+    if pairs:
+      return len(pairs)
+  except OSError:
+    pass
+  return max(1, (os.cpu_count() or 2) // 2)
 
-  def one():
-    data, _, _, _ = ring.get_next(B, T)
-    return agent.train(dict(step_type=data[0], observation=data[1], action=data[2],
-                            reward=data[4], discount=data[5]))
 
-  # use the thread count that is fastest on this host (all cores is not always best for the
-  # small conv/matmul shapes of a batch-256 step); each candidate is timed on one warm step.
-  best, best_dt = cores, None
-  for nt in sorted({cores, min(cores, 64), min(cores, 32), min(cores, 16)}, reverse=True):
-    torch.set_num_threads(nt)
-    one()
+def _host_ram_gb():
+  try:
+    for line in open('/proc/meminfo'):
+      if line.startswith('MemAvailable'):
+        return int(line.split()[1]) / 1e6
+  except OSError:
+    pass
+  return 0.0
+
+
+class CpuArm(object):
+  """The CPU restatement of one step: numpy ring gather (oracle/replay.py) + torch-CPU train
+  (oracle/dqn_torch.py).  1 M-slot ring (256 x 4096, 29.6 GB) when the host has >= 48 GB
+  available, else the largest power-of-two ring that fits in a quarter of it."""
+
+  def __init__(self, seed=0):
+    import torch
+    from oracle import dqn_torch
+    from oracle import replay as oreplay
+    rng = np.random.RandomState(seed)
+    avail = _host_ram_gb()
+    b_env, l = B_ENV, L
+    while b_env * l * ROW_BYTES / 1e9 > max(avail - 18.0, avail * 0.25) and l > 64:
+      l //= 2
+    self.b_env, self.l = b_env, l
+    shapes = [(), (84, 84, 4), (), (), (), ()]
+    dtypes = [np.int32, np.uint8, np.int32, np.int32, np.float32, np.float32]
+    self.ring = oreplay.UniformReplayOracle(shapes, dtypes, b_env, l, seed=seed)
+    obs = self.ring.storage[1]
+    block = rng.randint(0, 256, size=(min(2048, obs.shape[0]),) + obs.shape[1:], dtype=np.uint8)
+    for i in range(0, obs.shape[0], block.shape[0]):           # tile a 58 MB random block
+      n = min(block.shape[0], obs.shape[0] - i)
+      obs[i:i + n] = block[:n]
+    cap = self.ring.capacity
+    self.ring.storage[0][...] = rng.randint(0, 3, size=cap)
+    self.ring.storage[2][...] = rng.randint(0, A, size=cap)
+    self.ring.storage[4][...] = rng.rand(cap)
+    self.ring.storage[5][...] = (rng.rand(cap) > 0.1)
+    self.ring.last_id = 2 * l + 17
+    self.agent = dqn_torch.DqnTorchOracle(_mnih_layers(rng))
+    self.torch = torch
+    self.threads = min(_physical_cores(), os.cpu_count() or 1)
+    torch.set_num_threads(self.threads)
+
+  def step(self):
+    data, _, _, _ = self.ring.get_next(B, T)
+    return self.agent.train(dict(step_type=data[0], observation=data[1], action=data[2],
+                                 reward=data[4], discount=data[5]))
+
+  def time_block(self, steps):
     t0 = time.perf_counter()
-    one()
-    dt = time.perf_counter() - t0
-    if best_dt is None or dt < best_dt:
-      best, best_dt = nt, dt
-  torch.set_num_threads(best)
-  cores = best
-  for _ in range(warmup):
-    one()
-  t0 = time.perf_counter()
-  for _ in range(steps):
-    one()
-  dt = time.perf_counter() - t0
-  sample = (f'{steps} train steps (batch {B}, T={T}, Mnih15 net, torch-CPU restatement, '
-            f'{b_env}x{l}-slot host ring instead of 1M slots)')
-  return steps / dt, cores, sample
+    for _ in range(steps):
+      self.step()
+    return steps / (time.perf_counter() - t0)
+
+  def measure(self, steps, warmup, blocks=3):
+    """Returns (median steps/s at the fixed thread count, best-of-sweep dict, description)."""
+    for _ in range(max(3, warmup)):
+      self.step()
+    sps = sorted(self.time_block(steps) for _ in range(blocks))
+    med = sps[len(sps) // 2]
+    sweep = {}
+    for nt in sorted({max(1, self.threads // 2), 16, 32} - {self.threads}):
+      if nt <= (os.cpu_count() or 1):
+        self.torch.set_num_threads(nt)
+        self.step()
+        sweep[str(nt)] = self.time_block(max(2, steps // 2))
+    self.torch.set_num_threads(self.threads)
+    sample = (f'{blocks} blocks x {steps} train steps after {max(3, warmup)} warm-up steps (batch {B}, '
+              f'T={T}, Mnih15 net, torch-CPU restatement, {self.b_env}x{self.l}-slot host ring, '
+              f'{self.threads} threads = physical cores; median block)')
+    return med, sweep, sample
 
 
 class ClockSampler(object):
@@ -138,7 +188,7 @@ class ClockSampler(object):
     try:
       self.f = open(self.path, 'w')
       self.proc = subprocess.Popen(
-          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '100',
+          ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits', '-lms', '50',
            '-i', str(self.index)], stdout=self.f, stderr=subprocess.DEVNULL)
     except Exception:
       self.proc = None
@@ -182,17 +232,35 @@ def run_reference(args):
   if rank != 0:
     return
   steps = max(1, min(args.steps, 20))
-  sps, cores, sample = cpu_reference_steps(steps, min(args.warmup, 2))
+  warm = max(3, min(args.warmup, 5))
+  arm = CpuArm()
+  sps, sweep, sample = arm.measure(steps, warm)
   line = dict(
       impl='reference', metric='train steps/sec (DQN Atari-shape, batch 256)', value=sps,
-      unit='steps/s', n_gpus=args.gpus, steps=steps, warmup=min(args.warmup, 2),
+      unit='steps/s', n_gpus=args.gpus, steps=steps, warmup=warm,
       ms_per_step=1000.0 / sps, higher_is_better=True, scaling='weak', vs_baseline=None,
       dtype='f32', data='synthetic',
       config=dict(workload=WORKLOAD, global_batch=B, per_gpu_batch=B, num_actions=A,
+                  host_ring=f'{arm.b_env}x{arm.l}',
                   parallelism='cpu (host cores of the box, rank 0 only)'),
-      cpu_baseline=dict(value=sps, unit='steps/s', cores=cores, kind='port', sample=sample),
+      cpu_baseline=dict(value=sps, unit='steps/s', cores=arm.threads, kind='port', sample=sample,
+                        other_thread_counts=sweep, logical_cpus=os.cpu_count()),
       e2e=dict(value=sps, unit='steps/s', h2d_bytes_per_step=0, d2h_bytes_per_step=0))
   print(json.dumps(line), flush=True)
+
+
+def _oracle_layers(net, Ly):
+  layers = [dict(kind='cast_scale', divisor=255.0)]
+  for l in net.layers:
+    if isinstance(l, Ly.Conv2D):
+      layers.append(dict(kind='conv', w=l.kernel.cpu().numpy().copy(), b=l.bias.cpu().numpy().copy(),
+                         stride=l.stride, act=l.activation))
+    elif isinstance(l, Ly.Flatten):
+      layers.append(dict(kind='flatten'))
+    elif isinstance(l, Ly.Dense):
+      layers.append(dict(kind='dense', w=l.kernel.cpu().numpy().copy(), b=l.bias.cpu().numpy().copy(),
+                         act=l.activation))
+  return layers
 
 
 def main():
@@ -200,9 +268,11 @@ def main():
   ap.add_argument('--gpus', type=int, default=1)
   ap.add_argument('--steps', type=int, default=200)
   ap.add_argument('--warmup', type=int, default=10)
+  ap.add_argument('--repeats', type=int, default=9)
   ap.add_argument('--impl', default='b200')
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
+  ap.add_argument('--no-extra', action='store_true', help='skip configs 1/3/4/5 and dp_parity')
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)
@@ -216,6 +286,7 @@ def main():
   from agents_b200.networks import q_network
   from agents_b200.replay_buffers import tf_uniform_replay_buffer as rb_mod
   from agents_b200.specs import tensor_spec
+  from agents_b200.train.utils import strategy_utils
   from agents_b200.trajectories import time_step as ts
   from agents_b200.trajectories import trajectory
   from agents_b200.utils import common
@@ -229,9 +300,25 @@ def main():
   dev = torch.device('cuda', local_rank)
   if world > 1:
     dist.init_process_group('nccl', device_id=dev)
+  strategy = strategy_utils.get_strategy()
   W = max(args.warmup, 3)
   K = args.steps
+  R = max(1, args.repeats)
   peaks = _peaks()
+  extra = {}
+
+  def guarded(name, fn):
+    try:
+      extra[name] = fn()
+    except Exception as e:  # pylint: disable=broad-except
+      extra[name] = dict(error=f'{type(e).__name__}: {e}')
+      sys.stderr.write(f'[rank {rank}] {name} failed: {type(e).__name__}: {e}\n')
+    torch.cuda.synchronize()
+
+  # ---- data-parallel parity first (small, eager; uses the process group before any graph) -------
+  if world > 1 and not args.no_extra:
+    from profiles import configs
+    guarded('dp_parity', lambda: configs.dp_parity(strategy, dev))
 
   # ---- build the workload ---------------------------------------------------------------------
   obs_spec = tensor_spec.TensorSpec((84, 84, 4), torch.uint8, 'observation')
@@ -268,6 +355,28 @@ def main():
                                                 last_id - last_id % L - L + pos))
   rb._last_id.fill_(last_id)
   rb._last_id_host = last_id
+
+  # ---- parity at the bench config: 3 steps, GPU vs the CPU restatement on the same batches ------
+  parity = None
+  cpu_arm_layers = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    from oracle import dqn_torch
+    torch.set_num_threads(min(_physical_cores(), os.cpu_count() or 1))
+    orc = dqn_torch.DqnTorchOracle(_oracle_layers(net, Ly))
+    rels, last = [], None
+    for _ in range(3):
+      exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+      got = float(agent.train(exp).loss.item())
+      want = orc.train(dict(step_type=exp.step_type.cpu().numpy(), observation=exp.observation.cpu().numpy(),
+                            action=exp.action.cpu().numpy(), reward=exp.reward.cpu().numpy(),
+                            discount=exp.discount.cpu().numpy()))
+      rels.append(abs(got - want) / max(abs(want), 1e-12))
+      last = (got, want)
+    parity = dict(steps=3, max_rel_loss_err=max(rels), tolerance=1e-5, gpu_loss=last[0],
+                  oracle_loss=last[1], oracle='oracle/dqn_torch.py (torch CPU fp32, same initial weights, '
+                  'same sampled batches)', ok=bool(max(rels) <= 1e-5))
+    if not parity['ok']:
+      sys.stderr.write(f'PARITY FAILED at the bench config: {parity}\n')
 
   def step():
     exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
@@ -310,28 +419,38 @@ def main():
     fn()
   sync_all()
 
-  # ---- timed region: K steps, CUDA events, max over ranks ---------------------------------------
+  # ---- timed region: R blocks of K steps, CUDA events, max over ranks, median block -------------
   clocks = ClockSampler(local_rank)
   clocks.start()
-  e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-  sync_all()
-  e0.record()
-  for _ in range(K):
-    loss = fn()
-  e1.record()
-  sync_all()
-  ms = e0.elapsed_time(e1)
+  block_ms = []
+  t_wall0 = time.perf_counter()
+  for _ in range(R):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(K):
+      loss = fn()
+    e1.record()
+    sync_all()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+      t = torch.tensor([ms], device=dev, dtype=torch.float64)
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+      ms = float(t.item())
+    block_ms.append(ms)
+  # keep the sampler running over a load of at least ~1.5 s so that it sees the step's clocks
+  while time.perf_counter() - t_wall0 < 1.5:
+    for _ in range(K):
+      fn()
+    torch.cuda.synchronize()
   clk = clocks.stop()
-  if world > 1:
-    t = torch.tensor([ms], device=dev, dtype=torch.float64)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+  ms = float(np.median(block_ms))
   final_loss = float(loss.item())
   agent.check_numerics()
   steps_per_s = K / (ms / 1000.0)
   value = steps_per_s * world                  # batch-256-equivalent steps/s of the whole job
 
-  # ---- per-kernel timing for the rooflines (eager, CUDA events on the launch stream) ------------
+  # ---- per-kernel timing for the rooflines (CUDA events on the launch stream) -------------------
   # 20 gather launches (fresh Philox rows, distinct outputs) captured in one graph so that the
   # events bracket kernel time, not Python launch overhead; replayed 10x.
   n_g, reps = 20, 10
@@ -376,7 +495,7 @@ def main():
   update_tfs = FLOPS_PER_STEP / (update_ms * 1e-3) / 1e12
 
   # ---- e2e: host buffers in, loss out, every step -----------------------------------------------
-  Ke = max(10, min(K, 100))
+  Ke = max(10, min(K, 200))
   host = [torch.randint(0, 3, (B_ENV,), dtype=torch.int32).pin_memory(),
           torch.randint(0, 256, (B_ENV, 84, 84, 4), dtype=torch.uint8).pin_memory(),
           torch.randint(0, A, (B_ENV,), dtype=torch.int32).pin_memory(),
@@ -385,15 +504,22 @@ def main():
   h2d = sum(t.numel() * t.element_size() for t in host)
 
   # Double-buffered upload: the pinned->device copy of step i+1's frames runs on a copy stream
-  # while step i trains; every step still uploads its own inputs and reads its loss back.
+  # while step i trains.  The loss of every step is copied into its own pinned 4-byte slot right
+  # after the step (asynchronous D2H on the main stream + an event); the host reads step i-1's
+  # slot while step i runs, so the read-back never drains the pipeline and every loss is read.
   copy_stream = torch.cuda.Stream(device=dev)
   main_stream = torch.cuda.current_stream()
   staged = [[torch.empty_like(h, device=dev) for h in host] for _ in range(2)]
   ready = [torch.cuda.Event(), torch.cuda.Event()]
+  consumed = [torch.cuda.Event(), torch.cuda.Event()]
+  loss_slots = torch.zeros(2, dtype=torch.float32).pin_memory()
+  loss_done = [torch.cuda.Event(), torch.cuda.Event()]
+  losses_read = []
 
   def upload(i):
     slot = i & 1
     with torch.cuda.stream(copy_stream):
+      copy_stream.wait_event(consumed[slot])       # add_batch of step i-2 has read this slot
       for d, h in zip(staged[slot], host):
         d.copy_(h, non_blocking=True)
       ready[slot].record(copy_stream)
@@ -402,21 +528,32 @@ def main():
     slot = i & 1
     main_stream.wait_event(ready[slot])
     if not last:
-      upload(i + 1)   # slot (i+1)&1 was last read by step i-1, which ended with a host sync
+      upload(i + 1)
     d = staged[slot]
     rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
+    consumed[slot].record(main_stream)
     # get_next + train through common.function (the reference idiom: examples wrap
     # agent.train in common.function), i.e. the same captured step as `value`
-    return float(fn().item())                            # device -> host read of the result
+    out = fn()
+    loss_slots[slot:slot + 1].copy_(out.reshape(1), non_blocking=True)   # device -> pinned host
+    loss_done[slot].record(main_stream)
+    if i > 0:                                      # read the PREVIOUS step's loss while this one runs
+      loss_done[slot ^ 1].synchronize()
+      losses_read.append(float(loss_slots[slot ^ 1]))
 
+  for s in range(2):
+    consumed[s].record(main_stream)
   upload(0)
   for i in range(3):
     e2e_step(i, False)
   sync_all()
+  losses_read.clear()
   ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ee0.record()
   for i in range(Ke):
     e2e_step(3 + i, i == Ke - 1)
+  loss_done[(3 + Ke - 1) & 1].synchronize()        # the last step's loss is read inside the region
+  losses_read.append(float(loss_slots[(3 + Ke - 1) & 1]))
   ee1.record()
   sync_all()
   e2e_ms = ee0.elapsed_time(ee1)
@@ -425,28 +562,49 @@ def main():
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_ms = float(t.item())
   e2e_value = Ke / (e2e_ms / 1000.0) * world
+  assert len(losses_read) == Ke and all(np.isfinite(losses_read)), 'e2e loss read-back incomplete'
+
+  # ---- the other BASELINE configs (ring freed first: config 5 needs the HBM) --------------------
+  del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only
+  if use_graph:
+    del fn
+  torch.cuda.empty_cache()
+  if not args.no_extra:
+    from profiles import configs
+    guarded('gather_sweep', lambda: configs.gather_sweep(
+        dev, world, rank, peaks, caps_m=(1, 2, 4) if world == 1 else (1, 4, 8, 16)[:2 + (world >= 4) + (world >= 8)]))
+    guarded('ppo_update', lambda: configs.ppo_update(strategy, dev, peaks))
+    guarded('sac_step', lambda: configs.sac_step(strategy, dev, peaks))
+    if world == 1:
+      guarded('cartpole_iter', lambda: configs.cartpole_iter(dev))
 
   cpu = None
   if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    sps, cores, sample = cpu_reference_steps(8, 1)
-    cpu = dict(value=sps, unit='steps/s', cores=cores, kind='port', sample=sample)
+    arm = CpuArm()
+    sps, sweep, sample = arm.measure(8, 3)
+    cpu = dict(value=sps, unit='steps/s', cores=arm.threads, kind='port', sample=sample,
+               other_thread_counts=sweep, logical_cpus=os.cpu_count())
 
   if rank == 0:
     line = dict(
         metric='train steps/sec (DQN Atari-shape, batch 256)', value=value, unit='steps/s',
-        n_gpus=world, steps=K, warmup=W, ms_per_step=ms / K, higher_is_better=True,
+        n_gpus=world, steps=K, warmup=W, repeats=R, ms_per_step=ms / K,
+        block_ms=[round(b, 4) for b in block_ms], higher_is_better=True,
         scaling='weak', vs_baseline=None, dtype='f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)', data='synthetic',
         config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, num_actions=A,
                     parallelism=f'dp{world}' if world > 1 else 'single',
                     l2='inputs > L2: 29.6 GB ring, fresh random rows every step',
                     cuda_graph=bool(use_graph), collect_frames_per_e2e_step=B_ENV,
+                    timing=f'median of {R} blocks of {K} graph replays, each block bracketed by '
+                           'barrier + synchronize, CUDA events, max over ranks',
                     e2e_pipeline='pinned host frames -> double-buffered H2D on a copy stream -> '
-                                 'add_batch -> common.function(get_next + train) -> loss.item()'),
+                                 'add_batch -> common.function(get_next + train) -> per-step loss '
+                                 'D2H into pinned slots, read one step behind'),
         clocks=clk,
         e2e=dict(value=e2e_value, unit='steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
-                 steps=Ke),
+                 steps=Ke, losses_read=len(losses_read)),
         gpu_launches=int(launches_per_step * K),
-        roofline=dict(kernel='tc_gemm_kernel (Q-net conv/dense fwd+bwd, tcgen05 kind::tf32, 3xTF32)', bound='tensor',
+        roofline=dict(kernel='tc2_gemm_kernel / tc_gemm_kernel (Q-net conv/dense fwd+bwd, tcgen05 kind::tf32, 3xTF32)', bound='tensor',
                       achieved=update_tfs, peak=peaks['tensor'], unit='TFLOP/s',
                       frac=update_tfs / peaks['tensor'], traffic=traffic.get('update'),
                       peak_source=peaks['src'] + ' bf16 sustained', ms=update_ms,
@@ -460,8 +618,11 @@ def main():
                              traffic=traffic.get('gather'), peak_source=peaks['src'],
                              us=gather_ms * 1e3, algorithmic_bytes=GATHER_BYTES),
         final_loss=final_loss)
+    if parity is not None:
+      line['parity'] = parity
     if cpu is not None:
       line['cpu_baseline'] = cpu
+    line.update(extra)
     print(json.dumps(line), flush=True)
   if world > 1:
     # CUDA graphs that captured NCCL kernels make the communicator teardown hang on this stack:

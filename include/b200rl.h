@@ -327,6 +327,11 @@ int b200rl_set_gemm_mode(int mode);
 int b200rl_tc_debug_buffer(long long* dev_buf);
 /* Profiling/bring-up aid: selects an MN-major tile layout experiment (0 = production). */
 int b200rl_tc_debug_variant(int v);
+/* Second-generation GEMM kernel (tc2_gemm.cuh) switches.  bit 0: store an explicitly masked
+ * TF32 "hi" plane instead of using the raw fp32 operand tile for it (the tensor core ignores the
+ * low 13 mantissa bits; both settings are bit-identical, the default saves the store).  bit 1 (or B200RL_TC2=0 in the environment): route every GEMM to the
+ * first-generation kernel (A/B comparisons in profiles/tc2_check.py). */
+int b200rl_set_tc2_flags(int flags);
 
 /* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
  * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of

@@ -282,8 +282,9 @@ def test_kl_kernel_parity(cuda):
   out_kl = torch.empty(N, device=cuda)
   s = torch.empty(1, device=cuda)
   ws, nb = workspace.get(cuda)
-  _lib.call('b200rl_ppo_kl', _lib.ptr(d(lb)), _lib.ptr(d(sb)), A, _lib.ptr(d(la)), _lib.ptr(d(sa)), A,
-            _lib.ptr(d(w)), N, A, 1.0 / N, _lib.ptr(out_kl), _lib.ptr(s), _lib.ptr(ws), nb, _lib.stream())
+  t = [d(x) for x in (lb, sb, la, sa, w)]      # keep the device tensors alive across the launch
+  _lib.call('b200rl_ppo_kl', _lib.ptr(t[0]), _lib.ptr(t[1]), A, _lib.ptr(t[2]), _lib.ptr(t[3]), A,
+            _lib.ptr(t[4]), N, A, 1.0 / N, _lib.ptr(out_kl), _lib.ptr(s), _lib.ptr(ws), nb, _lib.stream())
   want = oppo.normal_kl(la, sa, lb, sb) * w
   np.testing.assert_allclose(out_kl.cpu().numpy(), want, rtol=1e-5, atol=1e-6)
   np.testing.assert_allclose(s.item(), want.mean(dtype=f32), rtol=1e-5)

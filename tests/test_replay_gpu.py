@@ -313,3 +313,27 @@ def test_full_size_properties(cuda):
     np.testing.assert_allclose(info.probabilities.cpu().numpy(),
                                np.float32(1.0) / np.float32((L - 1) * B_env), rtol=0)
   assert len(torch.unique(seg)) > 1
+
+
+def test_add_batch_inside_a_captured_step_keeps_the_host_mirror(cuda):
+  """`add_batch` replayed from a common.function graph advances the device-resident last_id; the
+  host mirror (used by gather_all / num_frames / the empty check) must follow every replay."""
+  from agents_b200.utils import common
+  rb = _scalar_rb(cuda, 3, max_length=16)
+  item = torch.zeros(3, dtype=torch.int64, device=cuda)
+
+  def step():
+    item.add_(1)
+    rb.add_batch(item)
+    return item
+
+  fn = common.function(step, warmup=1)
+  for _ in range(6):                       # 1 eager + capture/replay + 4 replays
+    fn()
+  torch.cuda.synchronize()
+  assert int(rb._last_id.item()) == 5 == rb._get_last_id()
+  assert int(rb.num_frames()) == 18
+  got = rb.gather_all().cpu().tolist()
+  assert got == [[1, 2, 3, 4, 5, 6]] * 3
+  data, _ = rb.get_next(sample_batch_size=4, num_steps=2)      # no spurious "buffer is empty"
+  assert tuple(data.shape) == (4, 2)

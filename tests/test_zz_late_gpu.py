@@ -102,8 +102,6 @@ def test_py_driver_feeds_the_ring(cuda):
   env.close()
 
 
-@pytest.mark.xfail(strict=False, reason='frame-dedup kernel and buffer were written without GPU access; '
-                                        'first executed by the round-end run')
 @pytest.mark.parametrize('K,L,adds', [(4, 16, 11), (4, 8, 29), (3, 8, 20), (2, 8, 9)])
 def test_frame_stack_buffer_rebuilds_the_stored_stacks(cuda, K, L, adds):
   """FrameStackReplayBuffer (one frame per slot) returns, for the ids it samples, exactly the
@@ -144,7 +142,11 @@ def test_frame_stack_buffer_rebuilds_the_stored_stacks(cuda, K, L, adds):
     env = data.action.cpu().numpy()                                  # action leaf = segment index
     got = data.observation.cpu().numpy()
     assert got.shape == (B, T, H, W, K) and ids.shape == (B, T)
-    assert (ids[:, 0] >= oldest + K - 1).all() and (ids[:, -1] <= adds - 1).all()
+    lo, hi = ofs.valid_range_ids(adds - 1, L, T, K)
+    assert (ids[:, 0] >= lo).all() and (ids[:, 0] < hi).all() and (ids[:, -1] <= adds - 1).all()
+    if adds <= L:
+      assert lo == 0                                                  # nothing excluded before the wrap
+    np.testing.assert_allclose(info.probabilities.cpu().numpy(), 1.0 / ((hi - lo) * B_env), rtol=1e-6)
     np.testing.assert_array_equal(data.reward.cpu().numpy(), ids.astype(f32))   # reward leaf = id
     for b in range(B):
       for t in range(T):
