@@ -65,6 +65,8 @@ SIGNATURES = {
     'b200rl_rb_write_rows': [ctypes.POINTER(Ring), _P, c_i64, _P, _P],
     'b200rl_rb_gather_all': [ctypes.POINTER(Ring), c_i64, _P, _P],
     'b200rl_rb_clear': [ctypes.POINTER(Ring), c_int, _P],
+    'b200rl_ep_assign': [_P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_i64, _P, _P, _P, _P, _P, c_int, c_int,
+                         _P, _P, _P],
     'b200rl_rb_draw': [ctypes.POINTER(Ring), c_i64, c_i64, c_u64, _P, _P, _P, _P],
     'b200rl_discounted_return': [_P, _P, _P, _P, c_i64, c_i64, c_int, c_int, _P],
     'b200rl_gae': [_P, _P, _P, _P, c_f32, _P, c_i64, c_i64, c_int, _P],
@@ -98,6 +100,7 @@ SIGNATURES = {
     'b200rl_tc_debug_buffer': [_P],
     'b200rl_tc_debug_variant': [c_int],
     'b200rl_set_tc2_flags': [c_int],
+    'b200rl_tc2_trace_buffer': [_P],
     'b200rl_dense_fwd': [_P, c_i64, _P, _P, _P, c_i64, c_i64, c_i64, c_int, _P, c_i64, _P],
     'b200rl_dense_bwd': [_P, c_i64, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_int, c_int, _P, c_i64,
                          _P],

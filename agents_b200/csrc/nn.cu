@@ -53,10 +53,12 @@ struct ARow {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = true;
+  static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[m * ld + k]; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return m * ld; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
+  __device__ __forceinline__ int64_t k_stride() const { return 1; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
@@ -66,10 +68,12 @@ struct ACol {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = false;
+  static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return m; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
+  __device__ __forceinline__ int64_t k_stride() const { return ld; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
@@ -80,10 +84,12 @@ struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   int64_t ld;
   static constexpr bool kNContig = true;
   static constexpr bool kKContig = false;
+  static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
   __device__ __forceinline__ int64_t row_off(int64_t n) const { return n; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k * ld; }
+  __device__ __forceinline__ int64_t k_stride() const { return ld; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
@@ -94,10 +100,12 @@ struct BCol {  // B(k, n) = p[n*ld + k]  (k contiguous)
   int64_t ld;
   static constexpr bool kNContig = false;
   static constexpr bool kKContig = true;
+  static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[n * ld + k]; }
   __device__ __forceinline__ int64_t row_off(int64_t n) const { return n * ld; }
   __device__ __forceinline__ int64_t k_off(int64_t k) const { return k; }
+  __device__ __forceinline__ int64_t k_stride() const { return 1; }
   __device__ __forceinline__ bool vec4_ok() const { return (ld & 3) == 0 && ((uintptr_t)p & 15) == 0; }
   __device__ __forceinline__ float ld1(int64_t off) const { return p[off]; }
   __device__ __forceinline__ float4 ld4(int64_t off) const { return *reinterpret_cast<const float4*>(p + off); }
@@ -168,6 +176,7 @@ template <typename T>
 struct AConv {
   ConvView<T> v;
   static constexpr bool kKContig = true;
+  static constexpr bool kLinearK = false;
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)m) + v.patch_offset((uint32_t)k));
@@ -183,6 +192,7 @@ template <typename T>
 struct AConvT {
   ConvView<T> v;
   static constexpr bool kKContig = false;
+  static constexpr bool kLinearK = false;
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
     return v.load(v.pos_offset((uint32_t)k) + v.patch_offset((uint32_t)m));
@@ -200,6 +210,7 @@ struct AConvT {
 struct AConvU8Raw {
   ConvView<uint8_t> v;
   static constexpr bool kKContig = true;
+  static constexpr bool kLinearK = false;
   static constexpr bool kExact = true;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.pos_offset((uint32_t)m); }
@@ -215,6 +226,7 @@ struct AConvU8Raw {
 struct AConvTU8Raw {
   ConvView<uint8_t> v;
   static constexpr bool kKContig = false;
+  static constexpr bool kLinearK = false;
   static constexpr bool kExact = true;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
   __device__ __forceinline__ int64_t row_off(int64_t m) const { return v.patch_offset((uint32_t)m); }
@@ -389,17 +401,23 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, float* __rest
   C[i] = v;
 }
 
-// dZ = dY * act'(Y)
+// dZ = dY * act'(Y); 16-byte accesses when n and the pointers allow (HBM-bound: 12 B / element)
 __global__ void act_bwd_kernel(const float* __restrict__ Y, const float* __restrict__ dY,
-                               float* __restrict__ dZ, int64_t n, int act) {
+                               float* __restrict__ dZ, int64_t n, int act, int vec) {
   pdl_prologue();
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float y = Y[i], g = dY[i];
-  float r = g;
-  if (act == B200RL_ACT_RELU) r = y > 0.f ? g : 0.f;
-  else if (act == B200RL_ACT_TANH) r = g * (1.f - y * y);
-  dZ[i] = r;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      const float4 y = reinterpret_cast<const float4*>(Y)[i];
+      const float4 g = reinterpret_cast<const float4*>(dY)[i];
+      reinterpret_cast<float4*>(dZ)[i] = make_float4(dact(y.x, g.x, act), dact(y.y, g.y, act),
+                                                     dact(y.z, g.z, act), dact(y.w, g.w, act));
+    }
+    return;
+  }
+  for (int64_t i = tid; i < n; i += stride) dZ[i] = dact(Y[i], dY[i], act);
 }
 
 // Column sums of dZ[M,N] in two deterministic stages.
@@ -442,6 +460,162 @@ __global__ void __launch_bounds__(256) colsum_final_kernel(const float* __restri
   for (int64_t p = lane; p < nparts; p += 32) s += part[p * N + n];
   s = warp_sum(s);
   if (lane == 0) db[n] = beta ? db[n] + s : s;
+}
+
+
+// ---------------------------------------------------------------------------------------
+// Skinny heads: Dense layers with N <= 16 outputs (Q head, value head, action means).
+// A tensor-core tile would be >= 87 % padding and the FFMA tiles need a split-K + reduce pair
+// for 256 rows; these three kernels are plain bandwidth-bound sweeps with W staged in shared
+// memory.  Used when the GEMM mode is not 0 (their weight gradient accumulates with atomics).
+// ---------------------------------------------------------------------------------------
+constexpr int kSkinnyMaxN = 16;
+constexpr int kSkinnySmem = 48 * 1024;
+
+// Y[m, :] = act(X[m, :] @ W + b): one warp per row, lanes stride over k, N shuffle reductions.
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_fwd_kernel(const float* __restrict__ X, int64_t ldx,
+                                                         const float* __restrict__ W,
+                                                         const float* __restrict__ bias,
+                                                         float* __restrict__ Y, int64_t M, int K,
+                                                         int N, int act) {
+  pdl_prologue();
+  extern __shared__ float sw[];                       // [K, N]
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) sw[i] = W[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int64_t m = (int64_t)blockIdx.x * nw + warp; m < M; m += (int64_t)gridDim.x * nw) {
+    float acc[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[n] = 0.f;
+    const float* x = X + m * ldx;
+#pragma unroll 4
+    for (int k = lane; k < K; k += 32) {
+      const float xv = x[k];
+      const float* w = sw + k * N;
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) acc[n] = fmaf(xv, w[n], acc[n]);
+    }
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n)
+      if (n < N) acc[n] = warp_sum(acc[n]);
+    if (lane == 0) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) Y[m * N + n] = apply_act(acc[n] + (bias ? bias[n] : 0.f), act);
+    }
+  }
+}
+
+// dX[m, k] = sum_n dY[m, n] W[k, n]  (* act'(X[m, k]) of the producing layer): 4 k per thread.
+template <int NMAX>
+__global__ void __launch_bounds__(256) skinny_dx_kernel(const float* __restrict__ dY,
+                                                        const float* __restrict__ W,
+                                                        float* __restrict__ dX, int64_t M, int K,
+                                                        int N, const ActMask mask) {
+  pdl_prologue();
+  extern __shared__ float sw[];                       // [K, N]
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) sw[i] = W[i];
+  __syncthreads();
+  const int kq = (K + 3) >> 2;                        // k quads per row
+  const int64_t total = M * kq;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t m = i / kq;
+    const int k0 = (int)(i - m * kq) * 4;
+    float dy[NMAX];
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) dy[n] = n < N ? dY[m * N + n] : 0.f;
+    float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (k0 + q < K) {
+        const float* w = sw + (k0 + q) * N;
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+          if (n < N) o[q] = fmaf(dy[n], w[n], o[q]);
+        if (mask.y) o[q] = dact(mask.y[m * mask.ld + k0 + q], o[q], mask.act);
+      }
+    }
+    float* dst = dX + m * K + k0;
+    if ((K & 3) == 0) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else
+      for (int q = 0; q < 4; ++q)
+        if (k0 + q < K) dst[q] = o[q];
+  }
+}
+
+// dW[k, n] += sum_m X[m, k] dY[m, n], db[n] += sum_m dY[m, n] over the CTA's slab of rows; thread
+// t owns input features k = t, t + blockDim, ...; the slab's dY rows are staged in shared memory.
+template <int NMAX, int KPT>
+__global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict__ X, int64_t ldx,
+                                                        const float* __restrict__ dY,
+                                                        float* __restrict__ dW,
+                                                        float* __restrict__ db, int64_t M, int K,
+                                                        int N, int64_t rows_per_cta) {
+  pdl_prologue();
+  constexpr int kChunk = 64;                          // rows of dY staged per step
+  __shared__ float sdy[kChunk * NMAX];
+  const int64_t mb = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t me = (mb + rows_per_cta < M) ? mb + rows_per_cta : M;
+  float acc[KPT][NMAX];
+#pragma unroll
+  for (int j = 0; j < KPT; ++j)
+#pragma unroll
+    for (int n = 0; n < NMAX; ++n) acc[j][n] = 0.f;
+  float bsum = 0.f;
+  for (int64_t m0 = mb; m0 < me; m0 += kChunk) {
+    const int rows = (int)((me - m0 < kChunk) ? me - m0 : kChunk);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * N; i += blockDim.x) sdy[(i / N) * NMAX + i % N] = dY[m0 * N + i];
+    __syncthreads();
+    if ((int)threadIdx.x < N)
+      for (int r = 0; r < rows; ++r) bsum += sdy[r * NMAX + threadIdx.x];
+#pragma unroll
+    for (int j = 0; j < KPT; ++j) {
+      const int k = threadIdx.x + j * blockDim.x;
+      if (k < K) {
+        const float* xp = X + m0 * ldx + k;
+        int r = 0;
+        for (; r + 4 <= rows; r += 4) {               // 4 independent loads in flight per thread
+          float xv[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) xv[u] = xp[(int64_t)(r + u) * ldx];
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int n = 0; n < NMAX; ++n)
+              if (n < N) acc[j][n] = fmaf(xv[u], sdy[(r + u) * NMAX + n], acc[j][n]);
+        }
+        for (; r < rows; ++r) {
+          const float xv = xp[(int64_t)r * ldx];
+#pragma unroll
+          for (int n = 0; n < NMAX; ++n)
+            if (n < N) acc[j][n] = fmaf(xv, sdy[r * NMAX + n], acc[j][n]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < KPT; ++j) {
+    const int k = threadIdx.x + j * blockDim.x;
+    if (k < K) {
+#pragma unroll
+      for (int n = 0; n < NMAX; ++n)
+        if (n < N) atomicAdd(dW + (int64_t)k * N + n, acc[j][n]);
+    }
+  }
+  if (db != nullptr && (int)threadIdx.x < N) atomicAdd(db + threadIdx.x, bsum);
+}
+
+static int skinny_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200RL_SKINNY");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 // col2im in gather form (deterministic): dX[n,y,x,c] = sum over kernel taps hitting (y,x).
@@ -644,6 +818,7 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   splits = (int)((g.K + kps - 1) / kps);
   if (splits < 1) splits = 1;
   const int64_t total = tiles * splits;
+  B200RL_CHECK_ARG(total < (1ll << 31), "tc2_gemm: too many work items");
   const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
   B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn);
   B200RL_CHECK_LAUNCH("tc2_gemm");
@@ -749,6 +924,53 @@ static int launch_grad_gemm(const AL& a, const BL& b, const GemmArgs& g, float* 
   return launch_tc_cfg<128, 3, 3, tc::EPI_ATOMIC>(a, b, g, none);
 }
 
+
+// ---- skinny-head dispatch (N <= 16) ----------------------------------------------------------
+static bool skinny_ok(int64_t M, int64_t K, int64_t N) {
+  return gemm_mode() != 0 && skinny_enabled() && N >= 1 && N <= kSkinnyMaxN && K >= 1 && K <= 1024 &&
+         K * N * (int64_t)sizeof(float) <= kSkinnySmem && M >= 1;
+}
+template <int NMAX>
+static int skinny_fwd_launch(const float* X, int64_t ldx, const float* W, const float* bias,
+                             float* Y, int64_t M, int64_t K, int64_t N, int act, cudaStream_t st) {
+  int64_t blocks = (M + 7) / 8;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  B200RL_LAUNCH(skinny_fwd_kernel<NMAX>, (unsigned)blocks, 256, (size_t)(K * N * sizeof(float)), st, X, ldx, W, bias, Y, M, (int)K, (int)N, act);
+  B200RL_CHECK_LAUNCH("skinny_fwd");
+  return B200RL_OK;
+}
+template <int NMAX>
+static int skinny_dx_launch(const float* dY, const float* W, float* dX, int64_t M, int64_t K,
+                            int64_t N, const ActMask& mask, cudaStream_t st) {
+  int64_t blocks = (M * ((K + 3) / 4) + 255) / 256;
+  if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
+  B200RL_LAUNCH(skinny_dx_kernel<NMAX>, (unsigned)blocks, 256, (size_t)(K * N * sizeof(float)), st, dY, W, dX, M, (int)K, (int)N, mask);
+  B200RL_CHECK_LAUNCH("skinny_dx");
+  return B200RL_OK;
+}
+template <int NMAX>
+static int skinny_dw_launch(const float* X, int64_t ldx, const float* dY, float* dW, float* db,
+                            int64_t M, int64_t K, int64_t N, int accumulate, cudaStream_t st) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dW, 0, (size_t)(K * N) * sizeof(float), st);
+    if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("skinny dW: memset failed: %s", cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+  }
+  int64_t rows = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);   // ~2 CTAs per SM; small M: 8-row slabs
+  rows = (rows + 7) / 8 * 8;
+  const int64_t blocks = (M + rows - 1) / rows;
+  if (K <= 256) B200RL_LAUNCH((skinny_dw_kernel<NMAX, 1>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
+  else if (K <= 512) B200RL_LAUNCH((skinny_dw_kernel<NMAX, 2>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
+  else B200RL_LAUNCH((skinny_dw_kernel<NMAX, 4>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
+  B200RL_CHECK_LAUNCH("skinny_dw");
+  return B200RL_OK;
+}
+#define SKINNY_BY_N(fn, N, ...)                                  \
+  ((N) <= 4 ? fn<4>(__VA_ARGS__) : (N) <= 8 ? fn<8>(__VA_ARGS__) : fn<16>(__VA_ARGS__))
+
 static int colsum(const float* dZ, float* db, int64_t M, int64_t N, int beta, void* ws,
                   int64_t ws_bytes, cudaStream_t st) {
   const int64_t nparts = (M + kColRows - 1) / kColRows;
@@ -808,6 +1030,15 @@ int b200rl_tc_debug_variant(int v) {
   return B200RL_OK;
 }
 
+int b200rl_tc2_trace_buffer(long long* dev_buf) {
+  cudaError_t e = cudaMemcpyToSymbol(tc2::g_tc2_trace, &dev_buf, sizeof(dev_buf));
+  if (e != cudaSuccess) {
+    set_error("tc2_trace_buffer: %s", cudaGetErrorString(e));
+    return B200RL_ERR_CUDA;
+  }
+  return B200RL_OK;
+}
+
 int b200rl_set_tc2_flags(int flags) {
   g_tc2_host_flags = flags;
   cudaError_t e = cudaMemcpyToSymbol(tc2::g_tc2_flags, &flags, sizeof(flags));
@@ -830,6 +1061,9 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
                      int64_t ws_bytes, void* stream) {
   B200RL_CHECK_ARG(X && W && Y, "dense_fwd: NULL argument");
   B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_fwd: ldx < K");
+  if (skinny_ok(M, K, N))
+    return SKINNY_BY_N(skinny_fwd_launch, N, X, ldx ? ldx : K, W, bias, Y, M, K, N, act,
+                       (cudaStream_t)stream);
   GemmArgs g{Y, bias, M, N, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
   return launch_gemm(ARow{X, ldx ? ldx : K}, BRow{W, N}, g);
 }
@@ -842,6 +1076,22 @@ int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* d
   B200RL_CHECK_ARG(x_act >= B200RL_ACT_NONE && x_act <= B200RL_ACT_TANH, "dense_bwd: x_act");
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
+  if (skinny_ok(M, K, N)) {
+    if (dX) {
+      ActMask mask{};
+      if (x_act != B200RL_ACT_NONE) mask = ActMask{X, ldx ? ldx : K, x_act};
+      rc = SKINNY_BY_N(skinny_dx_launch, N, dY, W, dX, M, K, N, mask, st);
+      if (rc) return rc;
+    }
+    if (dW) {
+      rc = SKINNY_BY_N(skinny_dw_launch, N, X, ldx ? ldx : K, dY, dW, db, M, K, N, accumulate, st);
+      if (rc) return rc;
+    } else if (db) {
+      rc = colsum(dY, db, M, N, accumulate, workspace, ws_bytes, st);
+      if (rc) return rc;
+    }
+    return B200RL_OK;
+  }
   if (dX) {
     GemmArgs g{dX, nullptr, M, K, N, B200RL_ACT_NONE, 0, workspace, ws_bytes, st};
     if (x_act != B200RL_ACT_NONE) g.mask = ActMask{X, ldx ? ldx : K, x_act};
@@ -865,7 +1115,10 @@ int b200rl_act_bwd(const float* Y, const float* dY, float* dZ, int64_t n, int ac
                    void* stream) {
   B200RL_CHECK_ARG(Y && dY && dZ && n >= 0, "act_bwd: bad argument");
   if (n == 0) return B200RL_OK;
-  B200RL_LAUNCH(act_bwd_kernel, (unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream, Y, dY, dZ, n, act);
+  const int vec = (n & 3) == 0 && ((((uintptr_t)Y | (uintptr_t)dY | (uintptr_t)dZ) & 15) == 0);
+  int64_t blocks = ((vec ? n / 4 : n) + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  B200RL_LAUNCH(act_bwd_kernel, (unsigned)blocks, 256, 0, (cudaStream_t)stream, Y, dY, dZ, n, act, vec);
   B200RL_CHECK_LAUNCH("act_bwd");
   return B200RL_OK;
 }

@@ -54,6 +54,24 @@ __global__ void __launch_bounds__(256) adam_tf_kernel(float* __restrict__ p,
   last_block_store(step, t);
 }
 
+__device__ __forceinline__ void rmsprop_one(float& p, float g, float& ms, float* mg, float& mom,
+                                            float lr, float decay, float momentum, float eps,
+                                            int centered) {
+  const float msi = ms + (g * g - ms) * (1.f - decay);
+  ms = msi;
+  float denom = msi + eps;
+  if (centered) {
+    const float mgi = *mg + (g - *mg) * (1.f - decay);
+    *mg = mgi;
+    denom = msi - mgi * mgi + eps;
+  }
+  const float mo = mom * momentum + lr * g * rsqrtf(denom);
+  mom = mo;
+  p = p - mo;
+}
+
+// 16-byte accesses when the buffers allow it (flat parameter buffers are 16 B aligned and padded
+// to 4 floats per variable): 44 B/param of traffic for the centered form, HBM-bound.
 __global__ void __launch_bounds__(256) rmsprop_tf_kernel(float* __restrict__ p,
                                                          const float* __restrict__ g,
                                                          float* __restrict__ ms,
@@ -61,24 +79,33 @@ __global__ void __launch_bounds__(256) rmsprop_tf_kernel(float* __restrict__ p,
                                                          float* __restrict__ mom, int64_t n,
                                                          float lr, float decay, float momentum,
                                                          float eps, int centered,
-                                                         const float* grad_scale) {
+                                                         const float* grad_scale, int vec) {
   pdl_prologue();
   const float gs = grad_scale ? *grad_scale : 1.f;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * gs;
-    const float msi = ms[i] + (gi * gi - ms[i]) * (1.f - decay);
-    ms[i] = msi;
-    float denom = msi + eps;
-    if (centered) {
-      const float mgi = mg[i] + (gi - mg[i]) * (1.f - decay);
-      mg[i] = mgi;
-      denom = msi - mgi * mgi + eps;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (vec) {
+    const int64_t n4 = n >> 2;
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 pv = reinterpret_cast<float4*>(p)[i];
+      const float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 msv = reinterpret_cast<float4*>(ms)[i];
+      float4 mgv = centered ? reinterpret_cast<float4*>(mg)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 mov = reinterpret_cast<float4*>(mom)[i];
+      rmsprop_one(pv.x, gv.x * gs, msv.x, &mgv.x, mov.x, lr, decay, momentum, eps, centered);
+      rmsprop_one(pv.y, gv.y * gs, msv.y, &mgv.y, mov.y, lr, decay, momentum, eps, centered);
+      rmsprop_one(pv.z, gv.z * gs, msv.z, &mgv.z, mov.z, lr, decay, momentum, eps, centered);
+      rmsprop_one(pv.w, gv.w * gs, msv.w, &mgv.w, mov.w, lr, decay, momentum, eps, centered);
+      reinterpret_cast<float4*>(p)[i] = pv;
+      reinterpret_cast<float4*>(ms)[i] = msv;
+      if (centered) reinterpret_cast<float4*>(mg)[i] = mgv;
+      reinterpret_cast<float4*>(mom)[i] = mov;
     }
-    const float mo = mom[i] * momentum + lr * gi * rsqrtf(denom);
-    mom[i] = mo;
-    p[i] = p[i] - mo;
+    return;
   }
+  for (int64_t i = tid; i < n; i += stride)
+    rmsprop_one(p[i], g[i] * gs, ms[i], centered ? mg + i : nullptr, mom[i], lr, decay, momentum, eps,
+                centered);
 }
 
 __global__ void __launch_bounds__(256) soft_update_kernel(float* __restrict__ target,
@@ -195,7 +222,9 @@ int b200rl_rmsprop_tf(float* p, const float* g, float* ms, float* mg, float* mom
   B200RL_CHECK_ARG(p && g && ms && mom && n >= 0, "rmsprop_tf: bad argument");
   B200RL_CHECK_ARG(!centered || mg, "rmsprop_tf: centered needs mg");
   if (n == 0) return B200RL_OK;
-  B200RL_LAUNCH(rmsprop_tf_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, p, g, ms, mg, mom, n, lr, decay, momentum, eps, centered, grad_scale_dev);
+  const int vec = (n & 3) == 0 && ((((uintptr_t)p | (uintptr_t)g | (uintptr_t)ms | (uintptr_t)mom |
+                                     (uintptr_t)(centered ? mg : p)) & 15) == 0);
+  B200RL_LAUNCH(rmsprop_tf_kernel, flat_grid(vec ? n / 4 : n), 256, 0, (cudaStream_t)stream, p, g, ms, mg, mom, n, lr, decay, momentum, eps, centered, grad_scale_dev, vec);
   B200RL_CHECK_LAUNCH("rmsprop_tf");
   return B200RL_OK;
 }

@@ -53,6 +53,18 @@ constexpr int kThreads = 13 * 32;
 // the explicitly masked hi plane on every layer (profiles/r2/run2_tc2_check*.jsonl).
 // bit 0 of the flags: store the masked hi plane anyway (A/B switch for tests/profiles).
 __device__ int g_tc2_flags = 0;
+// optional pipeline trace (b200rl_tc2_trace_buffer): CTA 0 stamps %globaltimer at the start and end
+// of every pipeline step of each role: trace[role][step][2], role 0 loader / 1 converter / 2 MMA /
+// 3 epilogue (steps are K blocks for roles 0-2 and tiles for role 3), first kTraceSteps steps.
+constexpr int kTraceSteps = 256;
+__device__ long long* g_tc2_trace = nullptr;
+__device__ __forceinline__ void trace(long long* tr, int role, uint32_t step, int which) {
+  if (tr != nullptr && step < kTraceSteps) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    tr[((int64_t)role * kTraceSteps + step) * 2 + which] = t;
+  }
+}
 
 template <int BN, int PASSES, bool A_EXACT>
 struct Layout {
@@ -96,6 +108,24 @@ __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
+// Waits of roles that have slack (loaders waiting for a free stage, the epilogue waiting for the
+// next accumulator): poll a few times, then sleep between polls so that the spinning warps do not
+// take issue slots from the converter / MMA warps of the same scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  int polls = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && ++polls > 4) __nanosleep(64);
+  } while (!done);
+}
+
 struct Work {
   int64_t m0, n0, kb, ke;
   int split, nkb;
@@ -104,13 +134,14 @@ struct Work {
 __device__ __forceinline__ Work decode_work(int64_t w, int64_t tiles_m, int64_t tiles_n, int BN,
                                             int64_t K, int64_t k_per_split) {
   Work o;
-  const int64_t tiles_mn = tiles_m * tiles_n;
-  const int64_t split = w / tiles_mn, rem = w - split * tiles_mn;
-  const int64_t tm = rem / tiles_n, tn = rem - tm * tiles_n;   // n fastest: neighbours share A rows
+  // 32-bit arithmetic (the host checks tiles * splits < 2^31): a 64-bit division is a call
+  const uint32_t tiles_mn = (uint32_t)(tiles_m * tiles_n), wi = (uint32_t)w, tn_ = (uint32_t)tiles_n;
+  const uint32_t split = wi / tiles_mn, rem = wi - split * tiles_mn;
+  const uint32_t tm = rem / tn_, tn = rem - tm * tn_;            // n fastest: neighbours share A rows
   o.split = (int)split;
-  o.m0 = tm * kBM;
-  o.n0 = tn * BN;
-  o.kb = split * k_per_split;
+  o.m0 = (int64_t)tm * kBM;
+  o.n0 = (int64_t)tn * BN;
+  o.kb = (int64_t)split * k_per_split;
   o.ke = (o.kb + k_per_split < K) ? o.kb + k_per_split : K;
   o.nkb = (int)((o.ke - o.kb + kBK - 1) / kBK);
   o.first_m = tm == 0;
@@ -119,11 +150,12 @@ __device__ __forceinline__ Work decode_work(int64_t w, int64_t tiles_m, int64_t 
 
 // ---- loaders ------------------------------------------------------------------------------------
 // K-contiguous fp32 view, ROWS x 32 tile: thread t owns chunk j = t & 7 (4 consecutive k) of rows
-// (t >> 3) + 16 i.  sw128(r0 + 16 i, j) = sw128(r0, j) + 2048 i.
+// (t >> 3) + 16 i.  sw128(r0 + 16 i, j) = sw128(r0, j) + 2048 i.  Row base POINTERS are hoisted per
+// tile; a K block costs one k_off and, per chunk, one 64-bit add + the LDGSTS.
 template <int ROWS, class V>
 struct LoadKContigF32 {
   static constexpr int NR = ROWS / 16;
-  int64_t roff[NR];
+  const char* rowp[NR];                            // element (row, 0); rows past the edge: row 0
   uint32_t ok, dst0;
   int j;
   __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
@@ -135,51 +167,62 @@ struct LoadKContigF32 {
     for (int i = 0; i < NR; ++i) {
       const int64_t r = row0 + r0 + 16 * i;
       const bool in = r < row_limit;
-      roff[i] = in ? v.row_off(r) : 0;
+      rowp[i] = reinterpret_cast<const char*>(v.addr(in ? v.row_off(r) : 0));
       ok |= (in ? 1u : 0u) << i;
     }
   }
   __device__ __forceinline__ void issue(const V& v, uint32_t plane, int64_t k0, int64_t ke) {
     const int64_t k = k0 + 4 * j;
     const bool kin = k < ke;                       // K % 4 == 0: a chunk is all in or all out
-    const int64_t koff = kin ? v.k_off(k) : 0;
+    const int64_t kbytes = kin ? v.k_off(k) * (int64_t)sizeof(float) : 0;
 #pragma unroll
-    for (int i = 0; i < NR; ++i) {
-      const bool in = kin && ((ok >> i) & 1u);
-      cp_async16(plane + dst0 + 2048u * i, v.addr(in ? roff[i] + koff : 0), in ? 16u : 0u);
-    }
+    for (int i = 0; i < NR; ++i)
+      cp_async16(plane + dst0 + 2048u * i, rowp[i] + kbytes, (kin && ((ok >> i) & 1u)) ? 16u : 0u);
   }
 };
 
 // MN-major fp32 view (the M/N index is contiguous in memory), 32 x ROWS tile: thread t owns row
-// chunk cm = t % CPR (rows 4cm..4cm+3) at k-rows t / CPR + KSTEP i.  k_off(k) of the conv
-// filter-gradient view is a full (n, oy, ox) decode: lane l computes it for k0 + l once and the
-// offsets are fetched by shuffle.
+// chunk cm = t % CPR (rows 4cm..4cm+3) at k-rows t / CPR + KSTEP i; the shared-memory offsets of
+// its chunks are fixed for the whole kernel.  Linear views (k_off = k * ld) step their pointer;
+// the conv filter-gradient view needs a full (n, oy, ox) decode per k: lane l computes it for
+// k0 + l once and the offsets are fetched by shuffle.
 template <int ROWS, class V>
 struct LoadMnF32 {
   static constexpr int CPR = ROWS / 4;
   static constexpr int KSTEP = kLoaderThreads / CPR;
   static constexpr int NC = 32 / KSTEP;            // chunks per thread
-  int64_t roff;
+  const char* rowp;
+  uint32_t dst[NC];
   bool ok;
-  int cm, kk0;
+  int kk0;
   __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
-    cm = t % CPR;
+    const int cm = t % CPR;
     kk0 = t / CPR;
     const int64_t r = row0 + 4 * cm;
     ok = r < row_limit;                            // rows % 4 == 0 (host check)
-    roff = ok ? v.row_off(r) : 0;
+    rowp = reinterpret_cast<const char*>(v.addr(ok ? v.row_off(r) : 0));
+#pragma unroll
+    for (int i = 0; i < NC; ++i) dst[i] = tc::mn128<ROWS>((uint32_t)cm, (uint32_t)(kk0 + KSTEP * i));
   }
   __device__ __forceinline__ void issue(const V& v, uint32_t plane, int64_t k0, int64_t ke) {
-    const int lane = threadIdx.x & 31;
-    const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
+    if constexpr (V::kLinearK) {
+      const int64_t step = v.k_stride() * (int64_t)sizeof(float);
+      const char* p = rowp + (k0 + kk0) * step;
 #pragma unroll
-    for (int i = 0; i < NC; ++i) {
-      const int kk = kk0 + KSTEP * i;
-      const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
-      const bool in = ok && (k0 + kk < ke);
-      cp_async16(plane + tc::mn128<ROWS>((uint32_t)cm, (uint32_t)kk),
-                 v.addr(in ? roff + koff : 0), in ? 16u : 0u);
+      for (int i = 0; i < NC; ++i) {
+        const bool in = ok && (k0 + kk0 + KSTEP * i < ke);
+        cp_async16(plane + dst[i], in ? p + (int64_t)(KSTEP * i) * step : rowp, in ? 16u : 0u);
+      }
+    } else {
+      const int lane = threadIdx.x & 31;
+      const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
+#pragma unroll
+      for (int i = 0; i < NC; ++i) {
+        const int kk = kk0 + KSTEP * i;
+        const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
+        const bool in = ok && (k0 + kk < ke);
+        cp_async16(plane + dst[i], rowp + (in ? koff : 0) * (int64_t)sizeof(float), in ? 16u : 0u);
+      }
     }
   }
 };
@@ -233,8 +276,9 @@ struct LoadMnU8 {
       const int kk = kk0 + 16 * i;
       const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
       const bool in = ok && (k0 + kk < ke);
-      cp_async16(raw + (uint32_t)kk * 128u + (uint32_t)c * 16u, v.addr(in ? roff + koff : 0),
-                 in ? 16u : 0u);
+      // slot c ^ 2(kk & 3): see convert_u8_mn
+      cp_async16(raw + (uint32_t)kk * 128u + (((uint32_t)c ^ (((uint32_t)kk & 3u) << 1)) << 4),
+                 v.addr(in ? roff + koff : 0), in ? 16u : 0u);
     }
   }
 };
@@ -265,11 +309,13 @@ __device__ __forceinline__ void convert_f32(uint32_t plane, uint32_t lo_off, int
     if (do_colsum) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
   }
 }
+// 4 packed uint8 -> 4 floats, exactly: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes the
+// 2^23 (2 full-rate instructions per pixel instead of shift + mask + I2F)
 __device__ __forceinline__ void u8x4_to_f32(uint32_t w, float4& o) {
-  o.x = (float)(w & 0xFFu);
-  o.y = (float)((w >> 8) & 0xFFu);
-  o.z = (float)((w >> 16) & 0xFFu);
-  o.w = (float)(w >> 24);
+  o.x = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7540)) - 8388608.f;
+  o.y = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7541)) - 8388608.f;
+  o.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
+  o.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
 }
 // raw [128 rows][32 B] uint8 -> K-major SWIZZLE_128B fp32 tile: thread t expands row t
 __device__ __forceinline__ void convert_u8_kcontig(uint32_t raw, uint32_t plane, int t) {
@@ -290,24 +336,31 @@ __device__ __forceinline__ void convert_u8_kcontig(uint32_t raw, uint32_t plane,
     }
   }
 }
-// raw [32 k][128 B] uint8 -> MN-major fp32 tile (128 rows): thread t expands 16-byte chunk c = t & 7
-// of k-rows (t >> 3) and (t >> 3) + 16, i.e. row chunks 4c..4c+3
+// raw [32 k][128 B] uint8 -> MN-major fp32 tile (128 rows).  Chunk (kk, c) = the 16 patch
+// elements 16c..16c+15 at reduction index kk sits in 16-byte slot c ^ 2(kk & 3) of raw row kk
+// (LoadMnU8 writes it there).  A quarter-warp = 4 consecutive kk x 2 neighbouring chunks: its
+// eight 16-byte reads hit eight different slots, and because lanes with odd c walk their four
+// float4 sub-chunks in the order q ^ 1, its eight stores land in the eight different 16-byte
+// slots of one 512 B atom of the SWIZZLE_128B_BASE32B layout -- no bank conflicts on either side.
 __device__ __forceinline__ void convert_u8_mn(uint32_t raw, uint32_t plane, int t) {
-  const int c = t & 7;
+  const uint32_t kin = (uint32_t)t & 3u, cb = ((uint32_t)t >> 2) & 1u;
+  const uint32_t c = ((((uint32_t)t >> 3) & 3u) << 1) | cb, kq = ((uint32_t)t >> 5) & 3u;
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
-    const int kk = (t >> 3) + 16 * i;
+    const uint32_t kk = ((kq + 4u * i) << 2) | kin;
     uint4 p;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
-                 : "r"(raw + (uint32_t)kk * 128u + (uint32_t)c * 16u)
+                 : "r"(raw + kk * 128u + ((c ^ (kin << 1)) << 4))
                  : "memory");
-    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
+    // sub-chunk order q ^ cb without dynamic register indexing
+    const uint32_t w0 = cb ? p.y : p.x, w1 = cb ? p.x : p.y, w2 = cb ? p.w : p.z, w3 = cb ? p.z : p.w;
+    const uint32_t w[4] = {w0, w1, w2, w3};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float4 o;
       u8x4_to_f32(w[q], o);
-      sts128(plane + tc::mn128<kBM>((uint32_t)(4 * c + q), (uint32_t)kk), o);
+      sts128(plane + tc::mn128<kBM>(4u * c + ((uint32_t)q ^ cb), kk), o);
     }
   }
 }
@@ -364,6 +417,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   pdl_wait();                                      // nothing above touched global memory
 
   const int64_t total = tiles_m * tiles_n * (int64_t)splits;
+  long long* const tr = blockIdx.x == 0 ? g_tc2_trace : nullptr;
   constexpr bool kLoA = PASSES == 3 && !AL::kExact;
   constexpr bool kLoB = PASSES == 3;
   constexpr uint32_t kOffB = L::kNumA * L::kATile;
@@ -381,12 +435,14 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
-        mbar_wait(smem_addr(&empty[s]), ph ^ 1u);
+        mbar_wait_relaxed(smem_addr(&empty[s]), ph ^ 1u);
+        if (tid == 0) trace(tr, 0, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         const int64_t k0 = wk.kb + (int64_t)kbi * kBK;
         la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
         lb.issue(b, st + kOffB, k0, wk.ke);
         cp_async_arrive(smem_addr(&raw_full[s]));
+        if (tid == 0) trace(tr, 0, it, 1);
       }
     }
   } else if (warp < 8) {
@@ -402,6 +458,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
         mbar_wait(smem_addr(&raw_full[s]), ph);
+        if (t == 0) trace(tr, 1, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
         if (AL::kExact) {
@@ -414,6 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           convert_f32<kLoB>(st + kOffB, L::kBTile, L::kBTile, t, raw_hi, csum, do_colsum);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_addr(&conv_full[s]));
+        if (t == 0) trace(tr, 1, it, 1);
       }
       if (do_colsum) {
         // Every chunk of a thread covers the same 4 columns (the MN-major atom layout repeats
@@ -450,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1u;
           mbar_wait(smem_addr(&conv_full[s]), ph);
+          trace(tr, 2, it, 0);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = smem_base + s * L::kStage, a_lo = a_hi + L::kATile;
@@ -477,6 +536,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
           }
           tc::tc_commit(smem_addr(&empty[s]));
+          trace(tr, 2, it, 1);
         }
         tc::tc_commit(smem_addr(&acc_full[buf]));
       }
@@ -489,7 +549,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
       const uint32_t buf = tl & 1u;
-      mbar_wait(smem_addr(&acc_full[buf]), (tl >> 1) & 1u);
+      mbar_wait_relaxed(smem_addr(&acc_full[buf]), (tl >> 1) & 1u);
+      if (warp == kFirstEpiWarp && lane == 0) trace(tr, 3, tl, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t m = wk.m0 + q * 32 + lane;
       float* out = (splits > 1 && EPI == EPI_STORE) ? ws + (int64_t)wk.split * M * N : C;
@@ -608,6 +669,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_addr(&acc_empty[buf]));
+      if (warp == kFirstEpiWarp && lane == 0) trace(tr, 3, tl, 1);
     }
   }
   __syncthreads();

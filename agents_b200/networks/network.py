@@ -238,7 +238,11 @@ class Network(object):
         dy = l.backward(x, y, dy, need_dx=need_dx)       # Flatten: reshape, flag carries through
         continue
       dz = dy.contiguous() if dy_is_preact else l.backward_act(y, dy)
-      x_act = producer_act(i) if need_dx and _FUSE_ACT_BWD else _ACT_NONE
+      # Dense consumers fold act'(x) into their dX epilogue (one coalesced read per output row);
+      # for Conv2D consumers the col2im epilogue would need a scattered read per red.add, which
+      # measured slower than the separate vectorised act_bwd pass (profiles/r2/README.md)
+      fuse = _FUSE_ACT_BWD == 2 or (_FUSE_ACT_BWD == 1 and isinstance(l, layers_lib.Dense))
+      x_act = producer_act(i) if need_dx and fuse else _ACT_NONE
       if side is not None:
         side.wait_stream(main)                   # dz (and everything before it) is ready
         dz.record_stream(side)
@@ -268,7 +272,7 @@ class Network(object):
 
 _BWD_OVERLAP = os.environ.get('B200RL_BWD_OVERLAP', '1') != '0'
 # act'(x) of the producing layer folded into the consumer's dX epilogue (0: separate act_bwd pass)
-_FUSE_ACT_BWD = os.environ.get('B200RL_FUSE_ACT_BWD', '1') != '0'
+_FUSE_ACT_BWD = int(os.environ.get('B200RL_FUSE_ACT_BWD', '1'))   # 0 never, 1 Dense consumers, 2 all
 _ACT_NONE = 0
 _SIDE_STREAMS = {}
 

@@ -524,7 +524,7 @@ def main():
         d.copy_(h, non_blocking=True)
       ready[slot].record(copy_stream)
 
-  def e2e_step(i, last):
+  def e2e_step(i, last, read_prev=True):
     slot = i & 1
     main_stream.wait_event(ready[slot])
     if not last:
@@ -537,7 +537,7 @@ def main():
     out = fn()
     loss_slots[slot:slot + 1].copy_(out.reshape(1), non_blocking=True)   # device -> pinned host
     loss_done[slot].record(main_stream)
-    if i > 0:                                      # read the PREVIOUS step's loss while this one runs
+    if read_prev:                                  # read the PREVIOUS step's loss while this one runs
       loss_done[slot ^ 1].synchronize()
       losses_read.append(float(loss_slots[slot ^ 1]))
 
@@ -545,13 +545,13 @@ def main():
     consumed[s].record(main_stream)
   upload(0)
   for i in range(3):
-    e2e_step(i, False)
+    e2e_step(i, False, read_prev=i > 0)
   sync_all()
   losses_read.clear()
   ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ee0.record()
-  for i in range(Ke):
-    e2e_step(3 + i, i == Ke - 1)
+  for i in range(Ke):                              # the first timed step has no timed predecessor
+    e2e_step(3 + i, i == Ke - 1, read_prev=i > 0)
   loss_done[(3 + Ke - 1) & 1].synchronize()        # the last step's loss is read inside the region
   losses_read.append(float(loss_slots[(3 + Ke - 1) & 1]))
   ee1.record()
@@ -572,7 +572,7 @@ def main():
   if not args.no_extra:
     from profiles import configs
     guarded('gather_sweep', lambda: configs.gather_sweep(
-        dev, world, rank, peaks, caps_m=(1, 2, 4) if world == 1 else (1, 4, 8, 16)[:2 + (world >= 4) + (world >= 8)]))
+        dev, world, rank, peaks, caps_m=(1, 2, 4) if world == 1 else ((1, 4, 8) if world == 2 else (1, 4, 8, 16))))
     guarded('ppo_update', lambda: configs.ppo_update(strategy, dev, peaks))
     guarded('sac_step', lambda: configs.sac_step(strategy, dev, peaks))
     if world == 1:

@@ -190,6 +190,25 @@ int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt, const float* nex
                        float* dq, int32_t* nan_flag, void* stream);
 
 /* ------------------------------------------------------------------------------------
+ * Episodic replay buffer bookkeeping -- replay_buffers/episodic_replay_buffer.py.
+ * An episode slot owns rows [slot*max_len, (slot+1)*max_len) of the leaf storage; row
+ * capacity*max_len is a trash row for items whose episode id is stale.
+ * ------------------------------------------------------------------------------------ */
+/* One launch = `_get_batch_episode_ids` (:1109-1187: ids < 0 or with begin[i] get consecutive new
+ * ids in item order, their slots are reset) + `_maybe_end_batch_episodes` (:1015-1045) + the
+ * length bump of add_batch / add_sequence / extend_episodes (:332-463, :1336-1414).  steps (per
+ * item) or steps_all rows are reserved per valid item and their first storage row is returned in
+ * out_rows (the trash row for stale ids or when max_len would be exceeded; *overflow = 1 then).
+ * All arrays are device pointers; begin / end / mask / steps / num_writes / out_rows / overflow
+ * may be NULL. */
+int b200rl_ep_assign(int64_t* episode_ids, const uint8_t* begin, const uint8_t* end,
+                     const uint8_t* mask, const int64_t* steps, int64_t steps_all, int64_t N,
+                     int64_t capacity, int64_t max_len, int64_t* last_episode, int64_t* loc_to_id,
+                     int64_t* lengths, uint8_t* completed, int64_t* num_writes, int bump_writes,
+                     int set_completed_from_end, int64_t* out_rows, int32_t* overflow,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------
  * PPO update math — agents/ppo/ppo_agent.py, ppo_utils.py, utils/tensor_normalizer.py
  * ------------------------------------------------------------------------------------ */
 /* Fused clipped-surrogate / value / entropy losses + gradients over N = B*T elements
@@ -332,6 +351,9 @@ int b200rl_tc_debug_variant(int v);
  * low 13 mantissa bits; both settings are bit-identical, the default saves the store).  bit 1 (or B200RL_TC2=0 in the environment): route every GEMM to the
  * first-generation kernel (A/B comparisons in profiles/tc2_check.py). */
 int b200rl_set_tc2_flags(int flags);
+/* Profiling aid: CTA 0 of every tc2 GEMM stamps %globaltimer at the start/end of each pipeline
+ * step of each role into dev_buf[4 roles][256 steps][2] (int64); NULL switches it off. */
+int b200rl_tc2_trace_buffer(long long* dev_buf);
 
 /* Y[M,N] = act(X[M,K] @ W[K,N] + bias[N]).  ldx = row stride of X in elements (0 -> K), so a
  * [B,T,K] batch can be read at a fixed t without a copy.  workspace: device scratch of
