@@ -94,8 +94,8 @@ SIGNATURES = {
     'b200rl_sac_alpha_loss': [_P, _P, _P, c_i64, c_f32, c_int, c_f32, c_f32, _P, _P, _P, _P],
     'b200rl_concat2': [_P, c_i64, c_i64, _P, c_i64, c_i64, c_i64, _P, _P],
     'b200rl_nstep_reduce': [_P, _P, c_f64, _P, _P, c_i64, c_i64, _P],
-    'b200rl_dqn_td_loss': [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_f64, c_f64,
-                           c_int, c_f32, _P, _P, _P, _P, _P, _P],
+    'b200rl_dqn_td_loss': [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_i64, c_i64,
+                           c_f64, c_f64, c_int, c_f32, _P, _P, _P, _P, _P, _P],
     'b200rl_set_gemm_mode': [c_int],
     'b200rl_tc_debug_buffer': [_P],
     'b200rl_tc_debug_variant': [c_int],

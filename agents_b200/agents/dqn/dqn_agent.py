@@ -114,6 +114,10 @@ class DqnAgent(tf_agent.TFAgent):
     self._clip_offsets = None
     self.replicas = 1           # set by train.Learner for data-parallel runs
     self._grad_sync = None      # callable(flat_grads) installed by train.Learner
+    # gradient all-reduce in buckets of at least this many bytes, overlapped with the rest of the
+    # backward pass (0: one all-reduce after the backward pass)
+    self._bucket_bytes = int(os.environ.get('B200RL_GRAD_BUCKET_BYTES', str(1 << 20)))
+    self._comm_stream = torch.cuda.Stream(device=device)
 
   # ---- construction helpers -----------------------------------------------------------------
   def _check_action_spec(self, action_spec):
@@ -202,8 +206,9 @@ class DqnAgent(tf_agent.TFAgent):
     elif self._overlap_target and not torch.cuda.is_current_stream_capturing():
       workspace.mirror(q.device, 1)   # size the side-stream scratch for a later capture
     dev = q.device
-    actions = exp.action[:, 0].to(torch.int32).contiguous()
-    step0 = exp.step_type[:, 0].to(torch.int32).contiguous()
+    # [:, 0] columns of the [B, T] tensors are read in place (no gather/cast launches)
+    actions, a_stride = self._column0(exp.action)
+    step0, s_stride = self._column0(exp.step_type)
     rew = exp.reward.float().contiguous()
     disc = exp.discount.float().contiguous()
     if weights is not None:
@@ -216,8 +221,9 @@ class DqnAgent(tf_agent.TFAgent):
     td_error = torch.empty(B, dtype=torch.float32, device=dev)
     dq = torch.empty((B, self._num_actions), dtype=torch.float32, device=dev)
     _lib.call('b200rl_dqn_td_loss', _lib.ptr(q), _lib.ptr(next_t), _lib.ptr(next_sel),
-              _lib.ptr(next_mask), _lib.ptr(actions), _lib.ptr(step0), _lib.ptr(rew),
-              _lib.ptr(disc), _lib.ptr(weights), B, self._num_actions, T, float(self._gamma),
+              _lib.ptr(next_mask), _lib.dptr(actions), _lib.dptr(step0), _lib.ptr(rew),
+              _lib.ptr(disc), _lib.ptr(weights), a_stride, s_stride, B, self._num_actions, T,
+              float(self._gamma),
               float(self._reward_scale_factor), self._loss_kind, float(B * self.replicas),
               _lib.ptr(loss), _lib.ptr(td_loss), _lib.ptr(td_error), _lib.ptr(dq),
               _lib.ptr(self._nan_flag), _lib.stream())
@@ -227,6 +233,15 @@ class DqnAgent(tf_agent.TFAgent):
       _lib.call('b200rl_l2_sum', _lib.ptr(w), w.numel(), float(coef) / self.replicas,
                 _lib.ptr(loss), _lib.stream())
     return loss, td_loss, td_error, dq, tape, reg
+
+  @staticmethod
+  def _column0(t):
+    """(tensor, element stride) such that element b of column 0 of `t` [B, T] is
+    tensor.data_ptr()[b * stride]; int32 storage is used as is, other dtypes are cast once."""
+    col = t[:, 0]
+    if col.dtype != torch.int32:
+      return col.to(torch.int32).contiguous(), 1
+    return col, (col.stride(0) if col.numel() > 1 else 1)
 
   def _loss(self, experience, td_errors_loss_fn=None, gamma=None, reward_scale_factor=None,
             weights=None, training=False):
@@ -239,13 +254,38 @@ class DqnAgent(tf_agent.TFAgent):
     loss, td_loss, td_error, dq, tape, reg = self._forward_loss(experience, weights,
                                                                 keep_tape=True)
     net = self._q_network
-    grads = net.backward(tape, dq)
+    # Data-parallel runs: start the all-reduce of the gradient tail (the fc layers come out of
+    # the backward pass first and hold 95 % of the bytes of the Atari net) on a communication
+    # stream as soon as it is complete, and reduce the small head after the last conv gradient.
+    bucketed = self._grad_sync is not None and self._bucket_bytes > 0 and not reg
+    hook = None
+    if bucketed:
+      total = net.flat_grads.numel()
+      state = {'lo': total, 'sent': total}
+      comm = self._comm_stream
+
+      def hook(lo, hi):
+        state['lo'] = min(state['lo'], lo)
+        if (state['sent'] - state['lo']) * 4 >= self._bucket_bytes:
+          cur = torch.cuda.current_stream()
+          comm.wait_stream(cur)
+          with torch.cuda.stream(comm):
+            self._grad_sync(net.flat_grads[state['lo']:state['sent']])
+          state['sent'] = state['lo']
+    grads = net.backward(tape, dq, grad_hook=hook)
+    if bucketed:
+      main = torch.cuda.current_stream()
+      if state['sent'] > 0:
+        self._comm_stream.wait_stream(main)
+        with torch.cuda.stream(self._comm_stream):
+          self._grad_sync(grads[0:state['sent']])
+      main.wait_stream(self._comm_stream)
     for coef, w in reg:  # d/dw coef*sum(w^2) = 2*coef*w
       off = w.data_ptr() - net.flat_params.data_ptr()
       g = grads[off // 4: off // 4 + w.numel()]
       _lib.call('b200rl_add_scaled', _lib.ptr(g), _lib.ptr(w), w.numel(),
                 2.0 * float(coef) / self.replicas, _lib.stream())
-    if self._grad_sync is not None:
+    if self._grad_sync is not None and not bucketed:
       self._grad_sync(grads)
     if self._gradient_clipping is not None:    # eager_utils.clip_gradient_norms, per variable
       if self._clip_offsets is None:

@@ -21,7 +21,8 @@ __global__ void __launch_bounds__(256) dqn_td_loss_kernel(
     const float* __restrict__ next_q_sel, const int32_t* __restrict__ next_mask,
     const int32_t* __restrict__ actions, const int32_t* __restrict__ step_type0,
     const float* __restrict__ traj_reward, const float* __restrict__ traj_discount,
-    const float* __restrict__ weights, int64_t B, int64_t A, int64_t T, float gamma,
+    const float* __restrict__ weights, int64_t action_stride, int64_t step_stride, int64_t B,
+    int64_t A, int64_t T, float gamma,
     float gamma_pow, float reward_scale, int loss_kind, float global_batch,
     float* __restrict__ loss, float* __restrict__ td_loss, float* __restrict__ td_error,
     float* __restrict__ dq, int32_t* __restrict__ nan_flag) {
@@ -51,7 +52,8 @@ __global__ void __launch_bounds__(256) dqn_td_loss_kernel(
       }
     }
     const float nq = next_q_tgt[b * A + best];
-    const int32_t act = actions[b];
+    int32_t act = actions[b * action_stride];
+    act = act < 0 ? 0 : (act >= A ? (int32_t)A - 1 : act);   // out-of-spec actions must not index past q
     const float qsa = q[b * A + act];
     const float rew = __fmul_rn(reward_scale, R);
     const float disc = __fmul_rn(gamma, D);
@@ -68,7 +70,7 @@ __global__ void __launch_bounds__(256) dqn_td_loss_kernel(
       l = __fmul_rn(e, e);
       dl_dq = -2.f * e;
     }
-    const float valid = (step_type0[b] == kStepLast) ? 0.f : 1.f;
+    const float valid = (step_type0[b * step_stride] == kStepLast) ? 0.f : 1.f;
     const float tl = __fmul_rn(valid, l);
     td_loss[b] = tl;
     td_error[b] = __fmul_rn(valid, e);
@@ -98,7 +100,8 @@ extern "C" int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt,
                                   const float* next_q_sel, const int32_t* next_mask,
                                   const int32_t* actions, const int32_t* step_type0,
                                   const float* traj_reward, const float* traj_discount,
-                                  const float* weights, int64_t B, int64_t A, int64_t T,
+                                  const float* weights, int64_t action_stride,
+                                  int64_t step_stride, int64_t B, int64_t A, int64_t T,
                                   double gamma, double reward_scale, int loss_kind,
                                   float global_batch, float* loss, float* td_loss,
                                   float* td_error, float* dq, int32_t* nan_flag, void* stream) {
@@ -110,7 +113,8 @@ extern "C" int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt,
   B200RL_CHECK_ARG(loss_kind == B200RL_LOSS_HUBER || loss_kind == B200RL_LOSS_SQUARED,
                    "dqn_td_loss: unknown loss kind %d", loss_kind);
   B200RL_CHECK_ARG(global_batch > 0.f, "dqn_td_loss: global_batch must be > 0");
-  B200RL_LAUNCH(dqn_td_loss_kernel, 1, 256, 0, (cudaStream_t)stream, q, next_q_tgt, next_q_sel, next_mask, actions, step_type0, traj_reward, traj_discount, weights, B, A, T, (float)gamma, (float)pow(gamma, (double)(T - 2)), (float)reward_scale, loss_kind, global_batch, loss, td_loss, td_error, dq, nan_flag);
+  B200RL_CHECK_ARG(action_stride >= 1 && step_stride >= 1, "dqn_td_loss: strides must be >= 1");
+  B200RL_LAUNCH(dqn_td_loss_kernel, 1, 256, 0, (cudaStream_t)stream, q, next_q_tgt, next_q_sel, next_mask, actions, step_type0, traj_reward, traj_discount, weights, action_stride, step_stride, B, A, T, (float)gamma, (float)pow(gamma, (double)(T - 2)), (float)reward_scale, loss_kind, global_batch, loss, td_loss, td_error, dq, nan_flag);
   B200RL_CHECK_LAUNCH("dqn_td_loss");
   return B200RL_OK;
 }

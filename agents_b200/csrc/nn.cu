@@ -15,8 +15,14 @@
 // Small output grids (fc layers, filter gradients) use deterministic split-K: partial tiles
 // go to the caller's workspace and a second kernel reduces them in fixed order and applies
 // bias + activation, so results are run-to-run bit-stable.
+#include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "common.cuh"
 
@@ -53,6 +59,7 @@ struct ARow {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = true;
+  static constexpr bool kTma2D = true;        // plain row-major [rows, K] matrix: TMA tile loads in tc2
   static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[m * ld + k]; }
@@ -68,6 +75,7 @@ struct ACol {
   const float* p;
   int64_t ld;
   static constexpr bool kKContig = false;
+  static constexpr bool kTma2D = false;        // plain row-major [rows, K] matrix: TMA tile loads in tc2
   static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return p[k * ld + m]; }
@@ -84,6 +92,7 @@ struct BRow {  // B(k, n) = p[k*ld + n]  (n contiguous)
   int64_t ld;
   static constexpr bool kNContig = true;
   static constexpr bool kKContig = false;
+  static constexpr bool kTma2D = false;        // plain row-major [rows, K] matrix: TMA tile loads in tc2
   static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[k * ld + n]; }
@@ -100,6 +109,7 @@ struct BCol {  // B(k, n) = p[n*ld + k]  (k contiguous)
   int64_t ld;
   static constexpr bool kNContig = false;
   static constexpr bool kKContig = true;
+  static constexpr bool kTma2D = true;        // plain row-major [rows, K] matrix: TMA tile loads in tc2
   static constexpr bool kLinearK = true;      // k_off(k) == k * k_stride()
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t k, int64_t n) const { return p[n * ld + k]; }
@@ -176,6 +186,7 @@ template <typename T>
 struct AConv {
   ConvView<T> v;
   static constexpr bool kKContig = true;
+  static constexpr bool kTma2D = false;
   static constexpr bool kLinearK = false;
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
@@ -192,6 +203,7 @@ template <typename T>
 struct AConvT {
   ConvView<T> v;
   static constexpr bool kKContig = false;
+  static constexpr bool kTma2D = false;
   static constexpr bool kLinearK = false;
   static constexpr bool kExact = false;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const {
@@ -210,6 +222,7 @@ struct AConvT {
 struct AConvU8Raw {
   ConvView<uint8_t> v;
   static constexpr bool kKContig = true;
+  static constexpr bool kTma2D = false;
   static constexpr bool kLinearK = false;
   static constexpr bool kExact = true;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
@@ -226,6 +239,7 @@ struct AConvU8Raw {
 struct AConvTU8Raw {
   ConvView<uint8_t> v;
   static constexpr bool kKContig = false;
+  static constexpr bool kTma2D = false;
   static constexpr bool kLinearK = false;
   static constexpr bool kExact = true;
   __device__ __forceinline__ float at(int64_t m, int64_t k) const { return 0.f; }
@@ -787,6 +801,75 @@ static bool tc2_ok(const AConvTU8Raw& v, int64_t rows, int64_t K) { return conv_
 template <class V>
 static bool tc2_ok(const V&, int64_t, int64_t) { return false; }   // AConv<uint8_t> with the exact division etc.
 
+
+// ---- TMA tensor maps for plain 2-D operands (tc2) ---------------------------------------------
+// cuTensorMapEncodeTiled is fetched through the runtime (no link against libcuda); maps are cached
+// by (base, rows, K, ld, box rows) because a training step re-launches the same GEMMs.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+// [rows, K] fp32, row stride ld elements, tile = box_rows x 32, SWIZZLE_128B (K-major operand tile)
+static int tmap_2d(const float* base, int64_t rows, int64_t K, int64_t ld, int box_rows,
+                   CUtensorMap* out) {
+  using Key = std::tuple<const void*, int64_t, int64_t, int64_t, int>;
+  static std::map<Key, CUtensorMap> cache;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  const Key key{base, rows, K, ld, box_rows};
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return B200RL_OK;
+  }
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) {
+    set_error("tc2: cuTensorMapEncodeTiled is not available from this driver");
+    return B200RL_ERR_UNSUPPORTED;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMap tm;
+  CUresult r = fn(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("tc2: cuTensorMapEncodeTiled failed (%d) for [%lld, %lld] ld %lld", (int)r,
+              (long long)rows, (long long)K, (long long)ld);
+    return B200RL_ERR_CUDA;
+  }
+  if (cache.size() > 4096) cache.clear();
+  cache[key] = tm;
+  *out = tm;
+  return B200RL_OK;
+}
+template <class V>
+static int tmap_for(const V&, int64_t, int64_t, int, CUtensorMap* out) {
+  memset(out, 0, sizeof(*out));
+  return B200RL_OK;
+}
+static int tmap_for(const ARow& v, int64_t rows, int64_t K, int box_rows, CUtensorMap* out) {
+  return tmap_2d(v.p, rows, K, v.ld, box_rows, out);
+}
+static int tmap_for(const BCol& v, int64_t rows, int64_t K, int box_rows, CUtensorMap* out) {
+  return tmap_2d(v.p, rows, K, v.ld, box_rows, out);
+}
+
 template <int BN, int PASSES, int EPI, class AL, class BL>
 static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
   using L = tc2::Layout<BN, PASSES, AL::kExact>;
@@ -820,7 +903,12 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   const int64_t total = tiles * splits;
   B200RL_CHECK_ARG(total < (1ll << 31), "tc2_gemm: too many work items");
   const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
-  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn);
+  CUtensorMap tmA, tmB;
+  int rc = tmap_for(a, g.M, g.K, tc::kBM, &tmA);
+  if (rc) return rc;
+  rc = tmap_for(b, g.N, g.K, BN, &tmB);
+  if (rc) return rc;
+  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, tmA, tmB);
   B200RL_CHECK_LAUNCH("tc2_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;

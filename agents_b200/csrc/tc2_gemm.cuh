@@ -19,13 +19,15 @@
 //                 conflict-free addressing, no global address arithmetic; they also accumulate
 //                 the fused bias gradient (column sums of B) of weight-gradient GEMMs;
 //   * warp 8      one thread issues tcgen05.mma into one of TWO TMEM accumulators;
-//   * warps 9-12  EPILOGUE of tile i (tcgen05.ld, bias/activation/act' mask, stores, split-K
+//   * warps 9-16  EPILOGUE of tile i (tcgen05.ld, bias/activation/act' mask, stores, split-K
 //                 red.add, fused col2im scatter-add) overlaps the main loop of tile i+1;
 //   * every loop that is not a fixed 4-8x unroll is rolled, the scalar fall-back paths live in
 //                 tc_gemm.cuh (the host dispatch only sends 16-byte-vectorisable views here).
 //
 // Shared-memory operand layouts, descriptors and the 3xTF32 scheme are those of tc_gemm.cuh.
 #pragma once
+#include <cuda.h>
+
 #include "tc_gemm.cuh"
 
 namespace b200rl {
@@ -46,7 +48,8 @@ constexpr int kLoaderThreads = 128;
 constexpr int kConvThreads = 128;
 constexpr int kMmaWarp = 8;
 constexpr int kFirstEpiWarp = 9;
-constexpr int kThreads = 13 * 32;
+constexpr int kEpiWarps = 8;          // two per TMEM lane quadrant, each drains half of the columns
+constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
 
 // The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32 tile IS the
 // hi plane and only the lo plane is computed (x - (x & 0xFFFFE000)); measured bit-identical to
@@ -283,6 +286,29 @@ struct LoadMnU8 {
   }
 };
 
+// Plain row-major 2-D fp32 operand (ARow / BCol: dense inputs, dY, W^T): ONE thread issues ONE
+// cp.async.bulk.tensor (TMA, SASS UTMALDG) per K block for the whole ROWS x 32 tile; the tensor
+// map's SWIZZLE_128B mode writes exactly the K-major layout the MMA descriptors expect, rows / k
+// past the matrix edge are zero-filled by the unit, and completion is counted in bytes on the same
+// mbarrier the other loader threads arrive on.
+template <int ROWS>
+struct LoadTma2D {
+  int32_t row0;
+  __device__ __forceinline__ void begin_tile(int64_t r0) { row0 = (int32_t)r0; }
+  __device__ __forceinline__ void issue(const CUtensorMap* tm, uint32_t plane, int64_t k0, uint32_t bar) {
+    if ((threadIdx.x & (kLoaderThreads - 1)) == 0) {
+      asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar),
+                   "r"((uint32_t)(ROWS * kBK * sizeof(float)))
+                   : "memory");
+      asm volatile(
+          "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes "
+          "[%0], [%1, {%2, %3}], [%4];" ::"r"(plane),
+          "l"(reinterpret_cast<uint64_t>(tm)), "r"((int32_t)k0), "r"(row0), "r"(bar)
+          : "memory");
+    }
+  }
+};
+
 template <int ROWS, class V, bool KCONTIG = V::kKContig, bool EXACT = V::kExact>
 struct LoaderFor;
 template <int ROWS, class V>
@@ -371,7 +397,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc2_gemm_kernel(const AL a, const BL b, const EpiArgs epi, float* __restrict__ C,
                     const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int act,
                     int beta, int splits, int64_t k_per_split, float* __restrict__ ws,
-                    float out_scale, int64_t tiles_m, int64_t tiles_n) {
+                    float out_scale, int64_t tiles_m, int64_t tiles_n,
+                    const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB) {
   using L = Layout<BN, PASSES, AL::kExact>;
   constexpr int S = L::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -398,7 +426,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_addr(&acc_full[i]), 1);
-      mbar_init(smem_addr(&acc_empty[i]), 4);
+      mbar_init(smem_addr(&acc_empty[i]), kEpiWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -427,11 +455,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ======================= loaders =======================
     typename LoaderFor<kBM, AL>::type la;
     typename LoaderFor<BN, BL>::type lb;
+    LoadTma2D<kBM> ta;                             // used instead of la / lb for plain 2-D operands
+    LoadTma2D<BN> tb;
+    const bool use_tma = (g_tc2_flags & 4) == 0;   // bit 2: cp.async loaders for those as well (A/B)
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
-      la.begin_tile(a, wk.m0, M, tid);
-      lb.begin_tile(b, wk.n0, N, tid);
+      if (AL::kTma2D && use_tma) ta.begin_tile(wk.m0);
+      else la.begin_tile(a, wk.m0, M, tid);
+      if (BL::kTma2D && use_tma) tb.begin_tile(wk.n0);
+      else lb.begin_tile(b, wk.n0, N, tid);
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
@@ -439,8 +472,11 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (tid == 0) trace(tr, 0, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         const int64_t k0 = wk.kb + (int64_t)kbi * kBK;
-        la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
-        lb.issue(b, st + kOffB, k0, wk.ke);
+        const uint32_t bar = smem_addr(&raw_full[s]);
+        if (AL::kTma2D && use_tma) ta.issue(&tmA, st, k0, bar);
+        else la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
+        if (BL::kTma2D && use_tma) tb.issue(&tmB, st + kOffB, k0, bar);
+        else lb.issue(b, st + kOffB, k0, wk.ke);
         cp_async_arrive(smem_addr(&raw_full[s]));
         if (tid == 0) trace(tr, 0, it, 1);
       }
@@ -497,6 +533,18 @@ __global__ void __launch_bounds__(kThreads, 1)
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(BN, !AL::kKContig, !BL::kKContig);
+      // One thread issues every MMA, so its scalar instruction stream IS the K-loop rate once the
+      // operands arrive (run 4 trace: 560 ns per K block, ~30 instructions per MMA, most of them
+      // rebuilding shared-memory descriptors).  Everything but the 14-bit start-address field of a
+      // descriptor is constant: keep the constants, and advance the start fields (16-byte units)
+      // with 32-bit adds.
+      constexpr uint32_t kaStep = AL::kKContig ? 2u : (2u * (kBM / 32) * 512u) >> 4;   // per K = 8
+      constexpr uint32_t kbStep = BL::kKContig ? 2u : (2u * (BN / 32) * 512u) >> 4;
+      constexpr uint32_t kStageStep = (uint32_t)L::kStage >> 4;
+      const uint64_t dA = AL::kKContig ? tc::make_desc(0) : tc::make_desc_mn(0, (kBM / 32) * 512u);
+      const uint64_t dB = BL::kKContig ? tc::make_desc(0) : tc::make_desc_mn(0, (BN / 32) * 512u);
+      const uint32_t fa_hi = smem_base >> 4, fa_lo = (smem_base + L::kATile) >> 4;
+      const uint32_t fb_hi = (smem_base + kOffB) >> 4, fb_lo = (smem_base + kOffB + L::kBTile) >> 4;
       uint32_t it = 0, tl = 0;
       for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
         const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
@@ -511,28 +559,21 @@ __global__ void __launch_bounds__(kThreads, 1)
           trace(tr, 2, it, 0);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = smem_base + s * L::kStage, a_lo = a_hi + L::kATile;
-          const uint32_t b_hi = a_hi + kOffB, b_lo = b_hi + L::kBTile;
+          const uint32_t so = s * kStageStep;
+          const uint32_t first = kbi == 0 ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < kBK / 8; ++ks) {
-            const uint32_t ka = AL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (kBM / 32) * 512u;
-            const uint32_t kbo = BL::kKContig ? (uint32_t)ks * 32u : (uint32_t)ks * 2u * (BN / 32) * 512u;
-            auto da = [&](uint32_t base) {
-              return AL::kKContig ? tc::make_desc(base + ka) : tc::make_desc_mn(base + ka, (kBM / 32) * 512u);
-            };
-            auto db = [&](uint32_t base) {
-              return BL::kKContig ? tc::make_desc(base + kbo) : tc::make_desc_mn(base + kbo, (BN / 32) * 512u);
-            };
-            const uint32_t first = (kbi == 0 && ks == 0) ? 0u : 1u;
+            const uint32_t oa = so + (uint32_t)ks * kaStep, ob = so + (uint32_t)ks * kbStep;
+            const uint32_t acc0 = ks == 0 ? first : 1u;
             if (PASSES == 3 && AL::kExact) {
-              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_lo), idesc, first);
-              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, 1u);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_lo + ob), idesc, acc0);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc, 1u);
             } else if (PASSES == 3) {
-              tc::tc_mma_tf32(tmem_d, da(a_lo), db(b_hi), idesc, first);
-              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_lo), idesc, 1u);
-              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, 1u);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_lo + oa), dB + (fb_hi + ob), idesc, acc0);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_lo + ob), idesc, 1u);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc, 1u);
             } else {
-              tc::tc_mma_tf32(tmem_d, da(a_hi), db(b_hi), idesc, first);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc, acc0);
             }
           }
           tc::tc_commit(smem_addr(&empty[s]));
@@ -544,7 +585,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncwarp();
   } else {
     // ======================= epilogue =======================
-    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int q = warp & 3;                        // TMEM lane quadrant this warp may read
+    const int chalf = (warp - kFirstEpiWarp) >> 2; // which half of the tile's columns it drains
     uint32_t tl = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
@@ -570,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (epi.mask.y) ybase = epi.mask.y + (int64_t)img * epi.mask.ld + in_off;
       }
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 16) {
+      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 16) {
         uint32_t r[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c;
         asm volatile(

@@ -180,6 +180,14 @@ class Network(object):
           l.init_params(gen)
     self._built = True
 
+  def _layer_range(self, layer):
+    """[lo, hi) of `layer`'s gradients inside the flat gradient buffer (elements)."""
+    first = layer.d_kernel
+    lo = (first.data_ptr() - self._grads.data_ptr()) // 4
+    last = layer.d_bias if getattr(layer, 'd_bias', None) is not None else layer.d_kernel
+    hi = (last.data_ptr() - self._grads.data_ptr()) // 4 + last.numel()
+    return lo, (hi + 3) // 4 * 4
+
   # ---- execution --------------------------------------------------------------------------
   def _run(self, x, keep):
     self._require_built()
@@ -201,8 +209,14 @@ class Network(object):
     """Forward that records activations; returns (output, tape)."""
     return self._run(observation, keep=True)
 
-  def backward(self, tape, dy, need_input_grad=False, need_param_grads=True):
+  def backward(self, tape, dy, need_input_grad=False, need_param_grads=True, grad_hook=None):
     """Back-propagates dLoss/d(output) through `tape`, OVERWRITING flat_grads.
+
+    grad_hook(lo, hi): called right after the parameter gradients of a layer have been enqueued,
+    with that layer's range of the flat gradient buffer, on the stream that produces them (the
+    side stream inside a captured graph).  Layers are visited last to first, so successive calls
+    cover a growing suffix of the buffer: data-parallel agents use it to start the gradient
+    all-reduce of the large tail (fc layers) while the convolution gradients are still running.
 
     need_input_grad: also return dLoss/d(input) (SAC's actor loss differentiates the critics
     w.r.t. their action input); need_param_grads=False skips the weight gradients (dense only).
@@ -251,6 +265,8 @@ class Network(object):
             self._grads.zero_()
             zeroed = True
           l.backward_parts(x, dz, need_dx=False, need_dw=True, accumulate=1)
+          if grad_hook is not None:
+            grad_hook(*self._layer_range(l))
         dy = l.backward_parts(x, dz, need_dx=True, need_dw=False, x_act=x_act) if need_dx else None
       elif not need_param_grads:
         if isinstance(l, layers_lib.Dense):
@@ -259,6 +275,8 @@ class Network(object):
           raise NotImplementedError('need_param_grads=False is only supported for Dense stacks.')
       else:
         dy = l.backward_parts(x, dz, need_dx=need_dx, need_dw=True, x_act=x_act, accumulate=1)
+        if grad_hook is not None:
+          grad_hook(*self._layer_range(l))
       dy_is_preact = x_act != _ACT_NONE
     if side is not None:
       main.wait_stream(side)

@@ -530,30 +530,46 @@ def main():
     if not last:
       upload(i + 1)
     d = staged[slot]
-    rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
-    consumed[slot].record(main_stream)
-    # get_next + train through common.function (the reference idiom: examples wrap
-    # agent.train in common.function), i.e. the same captured step as `value`
-    out = fn()
+    if e2e_fns is not None:
+      # add_batch + get_next + train of this staging slot replayed as ONE graph (one launch)
+      out = e2e_fns[slot]()
+      consumed[slot].record(main_stream)
+    else:
+      rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
+      consumed[slot].record(main_stream)
+      # get_next + train through common.function (the reference idiom: examples wrap
+      # agent.train in common.function), i.e. the same captured step as `value`
+      out = fn()
     loss_slots[slot:slot + 1].copy_(out.reshape(1), non_blocking=True)   # device -> pinned host
     loss_done[slot].record(main_stream)
     if read_prev:                                  # read the PREVIOUS step's loss while this one runs
       loss_done[slot ^ 1].synchronize()
       losses_read.append(float(loss_slots[slot ^ 1]))
 
+  def _fused(slot):
+    d = staged[slot]
+
+    def f():
+      rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
+      exp_, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+      return agent.train(exp_).loss
+    return common.function(f, warmup=1)
+
+  e2e_fns = [_fused(0), _fused(1)] if (use_graph and world == 1) else None
   for s in range(2):
     consumed[s].record(main_stream)
   upload(0)
-  for i in range(3):
+  n_pre = 5 if e2e_fns is not None else 3          # both slot graphs: eager call + capture each
+  for i in range(n_pre):
     e2e_step(i, False, read_prev=i > 0)
   sync_all()
   losses_read.clear()
   ee0, ee1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   ee0.record()
   for i in range(Ke):                              # the first timed step has no timed predecessor
-    e2e_step(3 + i, i == Ke - 1, read_prev=i > 0)
-  loss_done[(3 + Ke - 1) & 1].synchronize()        # the last step's loss is read inside the region
-  losses_read.append(float(loss_slots[(3 + Ke - 1) & 1]))
+    e2e_step(n_pre + i, i == Ke - 1, read_prev=i > 0)
+  loss_done[(n_pre + Ke - 1) & 1].synchronize()    # the last step's loss is read inside the region
+  losses_read.append(float(loss_slots[(n_pre + Ke - 1) & 1]))
   ee1.record()
   sync_all()
   e2e_ms = ee0.elapsed_time(ee1)
@@ -565,7 +581,7 @@ def main():
   assert len(losses_read) == Ke and all(np.isfinite(losses_read)), 'e2e loss read-back incomplete'
 
   # ---- the other BASELINE configs (ring freed first: config 5 needs the HBM) --------------------
-  del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only
+  del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only, e2e_fns
   if use_graph:
     del fn
   torch.cuda.empty_cache()
@@ -598,7 +614,7 @@ def main():
                     timing=f'median of {R} blocks of {K} graph replays, each block bracketed by '
                            'barrier + synchronize, CUDA events, max over ranks',
                     e2e_pipeline='pinned host frames -> double-buffered H2D on a copy stream -> '
-                                 'add_batch -> common.function(get_next + train) -> per-step loss '
+                                 'common.function(add_batch + get_next + train) per staging slot -> per-step loss '
                                  'D2H into pinned slots, read one step behind'),
         clocks=clk,
         e2e=dict(value=e2e_value, unit='steps/s', h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,

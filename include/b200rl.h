@@ -175,6 +175,9 @@ int b200rl_nstep_reduce(const float* reward, const float* discount, double gamma
  *   next_q_sel[B,A] net that picks argmax  (== next_q_tgt for DQN, online Q(s_n) for DDQN)
  *   next_mask[B,A]  optional int32 action mask for the argmax (1 = allowed)
  *   step_type0[B]   int32 step type of the first frame (LAST=2 zeroes the loss)
+ *   action_stride / step_stride: element strides of `actions` / `step_type0`, so the [:, 0]
+ *                   columns of [B, T] trajectory tensors are read in place (1 when packed);
+ *                   actions outside [0, A) are clamped before they index q
  *   traj_reward/traj_discount [B,T] raw trajectory fields (T = n+1); n-step reduction fused.
  *   weights[B] optional.  global_batch: divisor of the loss sum (B * replicas).
  * Outputs: loss[0] (= sum(td_loss*w)/global_batch, no reg), td_loss[B], td_error[B],
@@ -184,8 +187,9 @@ int b200rl_nstep_reduce(const float* reward, const float* discount, double gamma
 int b200rl_dqn_td_loss(const float* q, const float* next_q_tgt, const float* next_q_sel,
                        const int32_t* next_mask, const int32_t* actions,
                        const int32_t* step_type0, const float* traj_reward,
-                       const float* traj_discount, const float* weights, int64_t B, int64_t A,
-                       int64_t T, double gamma, double reward_scale, int loss_kind,
+                       const float* traj_discount, const float* weights, int64_t action_stride,
+                       int64_t step_stride, int64_t B, int64_t A, int64_t T, double gamma,
+                       double reward_scale, int loss_kind,
                        float global_batch, float* loss, float* td_loss, float* td_error,
                        float* dq, int32_t* nan_flag, void* stream);
 
@@ -349,7 +353,8 @@ int b200rl_tc_debug_variant(int v);
 /* Second-generation GEMM kernel (tc2_gemm.cuh) switches.  bit 0: store an explicitly masked
  * TF32 "hi" plane instead of using the raw fp32 operand tile for it (the tensor core ignores the
  * low 13 mantissa bits; both settings are bit-identical, the default saves the store).  bit 1 (or B200RL_TC2=0 in the environment): route every GEMM to the
- * first-generation kernel (A/B comparisons in profiles/tc2_check.py). */
+ * first-generation kernel (A/B comparisons in profiles/tc2_check.py).  bit 2: load plain 2-D
+ * operands with cp.async like the im2col views instead of TMA tensor tiles. */
 int b200rl_set_tc2_flags(int flags);
 /* Profiling aid: CTA 0 of every tc2 GEMM stamps %globaltimer at the start/end of each pipeline
  * step of each role into dev_buf[4 roles][256 steps][2] (int64); NULL switches it off. */

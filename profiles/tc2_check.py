@@ -3,7 +3,7 @@ max relative difference and time of forward / dX / dW for the Mnih'15 layers (ba
 PPO (200,100) tanh MLP at 4096x128 rows and the SAC (256,256) critic at batch 1024.
 A progress line is flushed BEFORE every launch, so a hang names its culprit.
 
-    python profiles/tc2_check.py [--reps 20] [--flags 0]   # --flags 1: explicitly masked hi plane
+    python profiles/tc2_check.py [--reps 20] [--flags 0]   # --flags 1: explicitly masked hi plane; 4: no TMA
 """
 import argparse
 import json

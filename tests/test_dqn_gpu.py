@@ -144,7 +144,7 @@ def test_td_loss_kernel_parity(cuda, loss_kind, B, A, T):
     tq, tnt, tns, ta, ts0, tr, td_, tw, tm = map(d, (q, nt, ns, actions, st0, rew, disc, w, mask))
     _lib.call('b200rl_dqn_td_loss', _lib.ptr(tq), _lib.ptr(tnt), _lib.ptr(tns),
               _lib.ptr(tm) if use_m else None, _lib.ptr(ta), _lib.ptr(ts0), _lib.ptr(tr), _lib.ptr(td_),
-              _lib.ptr(tw) if use_w else None, B, A, T, 0.99, 0.5,
+              _lib.ptr(tw) if use_w else None, 1, 1, B, A, T, 0.99, 0.5,
               _lib.LOSS_HUBER if loss_kind == 'huber' else _lib.LOSS_SQUARED, float(B),
               _lib.ptr(loss), _lib.ptr(tdl), _lib.ptr(tde), _lib.ptr(dq), _lib.ptr(flag), _lib.stream())
     np.testing.assert_allclose(loss.item(), want['weighted'], rtol=1e-5)
