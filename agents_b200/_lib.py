@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libb200rl.so')
+# B200RL_LIB: an alternative build of the same library (profiles/ A/B runs of compile-time variants)
+LIB_PATH = os.environ.get('B200RL_LIB') or os.path.join(_HERE, 'lib', 'libb200rl.so')
 
 MAX_LEAVES = 24
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2

@@ -24,7 +24,7 @@ static int g_pdl = -1;
 int pdl_enabled() {
   if (g_pdl < 0) {
     const char* e = getenv("B200RL_PDL");
-    g_pdl = e ? (atoi(e) != 0) : 0;
+    g_pdl = e ? (atoi(e) != 0) : 1;   // on by default (B200RL_PDL=0 switches it off)
   }
   return g_pdl;
 }

@@ -579,6 +579,14 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
 #pragma unroll
     for (int n = 0; n < NMAX; ++n) acc[j][n] = 0.f;
   float bsum = 0.f;
+  // K < blockDim: the threads form G = blockDim / K' row groups (K' = K rounded up to a warp), group
+  // g takes rows g, g + G, ... of every staged chunk (run 12: 100 of 256 threads worked on the PPO
+  // heads); the groups meet in the atomics below.
+  const int kpad = (K + 31) & ~31;
+  const int G = (KPT == 1 && kpad < (int)blockDim.x) ? (int)blockDim.x / kpad : 1;
+  const int rg = G > 1 ? (int)threadIdx.x / kpad : 0;
+  const int kt = G > 1 ? (int)threadIdx.x - rg * kpad : (int)threadIdx.x;
+  const bool live = rg < G;
   for (int64_t m0 = mb; m0 < me; m0 += kChunk) {
     const int rows = (int)((me - m0 < kChunk) ? me - m0 : kChunk);
     __syncthreads();
@@ -588,21 +596,21 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
       for (int r = 0; r < rows; ++r) bsum += sdy[r * NMAX + threadIdx.x];
 #pragma unroll
     for (int j = 0; j < KPT; ++j) {
-      const int k = threadIdx.x + j * blockDim.x;
-      if (k < K) {
+      const int k = kt + j * blockDim.x;
+      if (k < K && live) {
         const float* xp = X + m0 * ldx + k;
-        int r = 0;
-        for (; r + 4 <= rows; r += 4) {               // 4 independent loads in flight per thread
+        int r = rg;
+        for (; r + 3 * G < rows; r += 4 * G) {        // 4 independent loads in flight per thread
           float xv[4];
 #pragma unroll
-          for (int u = 0; u < 4; ++u) xv[u] = xp[(int64_t)(r + u) * ldx];
+          for (int u = 0; u < 4; ++u) xv[u] = xp[(int64_t)(r + u * G) * ldx];
 #pragma unroll
           for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int n = 0; n < NMAX; ++n)
-              if (n < N) acc[j][n] = fmaf(xv[u], sdy[(r + u) * NMAX + n], acc[j][n]);
+              if (n < N) acc[j][n] = fmaf(xv[u], sdy[(r + u * G) * NMAX + n], acc[j][n]);
         }
-        for (; r < rows; ++r) {
+        for (; r < rows; r += G) {
           const float xv = xp[(int64_t)r * ldx];
 #pragma unroll
           for (int n = 0; n < NMAX; ++n)
@@ -613,14 +621,160 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
   }
 #pragma unroll
   for (int j = 0; j < KPT; ++j) {
-    const int k = threadIdx.x + j * blockDim.x;
-    if (k < K) {
+    const int k = kt + j * blockDim.x;
+    if (k < K && live) {
 #pragma unroll
       for (int n = 0; n < NMAX; ++n)
         if (n < N) atomicAdd(dW + (int64_t)k * N + n, acc[j][n]);
     }
   }
   if (db != nullptr && (int)threadIdx.x < N) atomicAdd(db + threadIdx.x, bsum);
+}
+
+// ---- thin-input layers (K <= 32: observation -> first hidden layer) ----------------------------
+// Run 12 (PPO, 524 288 rows): x[M,17] @ W[17,200] fell through to the first-generation tensor-core
+// kernel (K % 4 != 0) at ~900 us and its weight gradient to the FFMA GEMM at ~600 us, against an
+// HBM floor of 65 us (the [M,200] activation is written / read once).  Both are one outer product
+// per row: thread (cq, rg) owns output columns 4cq..4cq+3 for rows rg*8..rg*8+7 of every 32-row
+// chunk; the chunk of X sits in shared memory (broadcast reads), W / dW columns in registers or
+// shared memory, the wide operand moves as coalesced float4.
+constexpr int kThinMaxK = 32, kThinMaxN = 256, kThinRows = 32;
+
+__global__ void __launch_bounds__(256) thin_fwd_kernel(const float* __restrict__ X, int64_t ldx,
+                                                       const float* __restrict__ W,
+                                                       const float* __restrict__ bias,
+                                                       float* __restrict__ Y, int64_t M, int K,
+                                                       int N, int act, int64_t chunks) {
+  pdl_prologue();
+  extern __shared__ float4 thin_smem[];
+  const int KP = (K + 3) & ~3, nq = N >> 2;
+  float4* sw = thin_smem;                              // [KP][nq] (rows >= K are zero)
+  float* sx = reinterpret_cast<float*>(thin_smem + KP * nq);   // [kThinRows][KP]
+  for (int i = threadIdx.x; i < KP * nq; i += blockDim.x)
+    sw[i] = (i / nq) < K ? reinterpret_cast<const float4*>(W)[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  const int cq = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const bool active = cq < nq;
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias && active) b4 = reinterpret_cast<const float4*>(bias)[cq];
+  for (int64_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x) {
+    const int64_t m0 = chunk * kThinRows;
+    __syncthreads();
+    for (int i = threadIdx.x; i < kThinRows * KP; i += blockDim.x) {
+      const int r = i / KP, k = i - r * KP;
+      sx[i] = (m0 + r < M && k < K) ? X[(m0 + r) * ldx + k] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float4 acc[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) acc[r] = b4;
+    for (int k = 0; k < KP; k += 4) {
+      const float4 w0 = sw[(k + 0) * nq + cq], w1 = sw[(k + 1) * nq + cq];
+      const float4 w2 = sw[(k + 2) * nq + cq], w3 = sw[(k + 3) * nq + cq];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const float4 x = *reinterpret_cast<const float4*>(sx + (rg * 8 + r) * KP + k);
+        acc[r].x = fmaf(x.x, w0.x, acc[r].x); acc[r].y = fmaf(x.x, w0.y, acc[r].y);
+        acc[r].z = fmaf(x.x, w0.z, acc[r].z); acc[r].w = fmaf(x.x, w0.w, acc[r].w);
+        acc[r].x = fmaf(x.y, w1.x, acc[r].x); acc[r].y = fmaf(x.y, w1.y, acc[r].y);
+        acc[r].z = fmaf(x.y, w1.z, acc[r].z); acc[r].w = fmaf(x.y, w1.w, acc[r].w);
+        acc[r].x = fmaf(x.z, w2.x, acc[r].x); acc[r].y = fmaf(x.z, w2.y, acc[r].y);
+        acc[r].z = fmaf(x.z, w2.z, acc[r].z); acc[r].w = fmaf(x.z, w2.w, acc[r].w);
+        acc[r].x = fmaf(x.w, w3.x, acc[r].x); acc[r].y = fmaf(x.w, w3.y, acc[r].y);
+        acc[r].z = fmaf(x.w, w3.z, acc[r].z); acc[r].w = fmaf(x.w, w3.w, acc[r].w);
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int64_t m = m0 + rg * 8 + r;
+      if (m < M) {
+        float4 v = acc[r];
+        v.x = apply_act(v.x, act); v.y = apply_act(v.y, act);
+        v.z = apply_act(v.z, act); v.w = apply_act(v.w, act);
+        reinterpret_cast<float4*>(Y + m * N)[cq] = v;
+      }
+    }
+  }
+}
+
+// dW[K,N] += X^T dZ, db[N] += column sums of dZ over the CTA's row range.
+template <int KMAX>
+__global__ void __launch_bounds__(256) thin_dw_kernel(const float* __restrict__ X, int64_t ldx,
+                                                      const float* __restrict__ dZ,
+                                                      float* __restrict__ dW,
+                                                      float* __restrict__ db, int64_t M, int K,
+                                                      int N, int64_t rows_per_cta) {
+  pdl_prologue();
+  extern __shared__ float4 thin_smem[];
+  const int nq = N >> 2;
+  float* sx = reinterpret_cast<float*>(thin_smem);     // [kThinRows][KMAX]
+  float* sred = sx + kThinRows * KMAX;                 // [(K + 1)][N] cross-row-group sums
+  for (int i = threadIdx.x; i < (K + 1) * N; i += blockDim.x) sred[i] = 0.f;
+  const int cq = threadIdx.x & 63, rg = threadIdx.x >> 6;
+  const bool active = cq < nq;
+  float4 acc[KMAX], bsum = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < KMAX; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t mb = (int64_t)blockIdx.x * rows_per_cta;
+  const int64_t me = (mb + rows_per_cta < M) ? mb + rows_per_cta : M;
+  for (int64_t m0 = mb; m0 < me; m0 += kThinRows) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kThinRows * KMAX; i += blockDim.x) {
+      const int r = i / KMAX, k = i - r * KMAX;
+      sx[i] = (m0 + r < me && k < K) ? X[(m0 + r) * ldx + k] : 0.f;
+    }
+    __syncthreads();
+    if (!active) continue;
+    float4 dz[8];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int64_t m = m0 + rg * 8 + r;
+      dz[r] = m < me ? reinterpret_cast<const float4*>(dZ + m * N)[cq] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      bsum.x += dz[r].x; bsum.y += dz[r].y; bsum.z += dz[r].z; bsum.w += dz[r].w;
+      const float* xr = sx + (rg * 8 + r) * KMAX;
+#pragma unroll
+      for (int k = 0; k < KMAX; k += 4) {
+        const float4 x = *reinterpret_cast<const float4*>(xr + k);
+        acc[k + 0].x = fmaf(x.x, dz[r].x, acc[k + 0].x); acc[k + 0].y = fmaf(x.x, dz[r].y, acc[k + 0].y);
+        acc[k + 0].z = fmaf(x.x, dz[r].z, acc[k + 0].z); acc[k + 0].w = fmaf(x.x, dz[r].w, acc[k + 0].w);
+        acc[k + 1].x = fmaf(x.y, dz[r].x, acc[k + 1].x); acc[k + 1].y = fmaf(x.y, dz[r].y, acc[k + 1].y);
+        acc[k + 1].z = fmaf(x.y, dz[r].z, acc[k + 1].z); acc[k + 1].w = fmaf(x.y, dz[r].w, acc[k + 1].w);
+        acc[k + 2].x = fmaf(x.z, dz[r].x, acc[k + 2].x); acc[k + 2].y = fmaf(x.z, dz[r].y, acc[k + 2].y);
+        acc[k + 2].z = fmaf(x.z, dz[r].z, acc[k + 2].z); acc[k + 2].w = fmaf(x.z, dz[r].w, acc[k + 2].w);
+        acc[k + 3].x = fmaf(x.w, dz[r].x, acc[k + 3].x); acc[k + 3].y = fmaf(x.w, dz[r].y, acc[k + 3].y);
+        acc[k + 3].z = fmaf(x.w, dz[r].z, acc[k + 3].z); acc[k + 3].w = fmaf(x.w, dz[r].w, acc[k + 3].w);
+      }
+    }
+  }
+  __syncthreads();
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < KMAX; ++k) {
+      if (k < K) {
+        float* d = sred + k * N + 4 * cq;
+        atomicAdd(d + 0, acc[k].x); atomicAdd(d + 1, acc[k].y);
+        atomicAdd(d + 2, acc[k].z); atomicAdd(d + 3, acc[k].w);
+      }
+    }
+    float* d = sred + K * N + 4 * cq;
+    atomicAdd(d + 0, bsum.x); atomicAdd(d + 1, bsum.y); atomicAdd(d + 2, bsum.z); atomicAdd(d + 3, bsum.w);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < K * N; i += blockDim.x) atomicAdd(dW + i, sred[i]);
+  if (db != nullptr)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) atomicAdd(db + i, sred[K * N + i]);
+}
+
+static int thin_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200RL_THIN");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
 }
 
 static int skinny_enabled() {
@@ -778,6 +932,12 @@ static int tc2_enabled() {
   if (v < 0) {
     const char* e = getenv("B200RL_TC2");
     v = e ? atoi(e) : 1;
+    const char* f = getenv("B200RL_TC2_FLAGS");    // profiles/: A/B switches of tc2_gemm.cuh
+    if (f) {
+      const int flags = atoi(f);
+      g_tc2_host_flags = flags;
+      cudaMemcpyToSymbol(tc2::g_tc2_flags, &flags, sizeof(flags));
+    }
   }
   return v && !(g_tc2_host_flags & 2);
 }
@@ -908,7 +1068,11 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   if (rc) return rc;
   rc = tmap_for(b, g.N, g.K, BN, &tmB);
   if (rc) return rc;
-  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, tmA, tmB);
+  // epilogue-bound shapes (col2im scatter-add, short K loops) get all eight epilogue warps
+  static const int epi_env = [] { const char* e = getenv("B200RL_TC2_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  const int epi_warps = (epi_env == 4 || epi_env == 8) ? epi_env
+                        : (EPI == tc::EPI_COL2IM || kps <= 224) ? 8 : 4;
+  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, epi_warps, tmA, tmB);
   B200RL_CHECK_LAUNCH("tc2_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
@@ -1137,6 +1301,43 @@ int b200rl_set_tc2_flags(int flags) {
   return B200RL_OK;
 }
 
+// ---- thin-input dispatch (K <= 32, 16 < N <= 256, N % 4 == 0) -----------------------------------
+static bool thin_ok(const float* X, int64_t ldx, const float* W, int64_t M, int64_t K, int64_t N) {
+  return gemm_mode() != 0 && thin_enabled() && K >= 1 && K <= kThinMaxK && N > kSkinnyMaxN &&
+         N <= kThinMaxN && (N & 3) == 0 && M >= 1 && al16(W);
+}
+static int thin_fwd_launch(const float* X, int64_t ldx, const float* W, const float* bias, float* Y,
+                           int64_t M, int64_t K, int64_t N, int act, cudaStream_t st) {
+  const int64_t chunks = (M + kThinRows - 1) / kThinRows;
+  const int KP = ((int)K + 3) & ~3;
+  const size_t smem = (size_t)KP * N * sizeof(float) + (size_t)kThinRows * KP * sizeof(float);
+  const int64_t blocks = chunks < 4 * kNumSMs ? chunks : 4 * kNumSMs;
+  B200RL_LAUNCH(thin_fwd_kernel, (unsigned)blocks, 256, smem, st, X, ldx, W, bias, Y, M, (int)K, (int)N, act, chunks);
+  B200RL_CHECK_LAUNCH("thin_fwd");
+  return B200RL_OK;
+}
+static int thin_dw_launch(const float* X, int64_t ldx, const float* dZ, float* dW, float* db,
+                          int64_t M, int64_t K, int64_t N, int accumulate, cudaStream_t st) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(dW, 0, (size_t)(K * N) * sizeof(float), st);
+    if (e == cudaSuccess && db) e = cudaMemsetAsync(db, 0, (size_t)N * sizeof(float), st);
+    if (e != cudaSuccess) {
+      set_error("thin dW: memset failed: %s", cudaGetErrorString(e));
+      return B200RL_ERR_CUDA;
+    }
+  }
+  int64_t rows = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  rows = (rows + kThinRows - 1) / kThinRows * kThinRows;
+  const int64_t blocks = (M + rows - 1) / rows;
+  const int KMAX = K <= 8 ? 8 : K <= 20 ? 20 : 32;
+  const size_t smem = ((size_t)kThinRows * KMAX + (size_t)(K + 1) * N) * sizeof(float);
+  if (KMAX == 8) B200RL_LAUNCH(thin_dw_kernel<8>, (unsigned)blocks, 256, smem, st, X, ldx, dZ, dW, db, M, (int)K, (int)N, rows);
+  else if (KMAX == 20) B200RL_LAUNCH(thin_dw_kernel<20>, (unsigned)blocks, 256, smem, st, X, ldx, dZ, dW, db, M, (int)K, (int)N, rows);
+  else B200RL_LAUNCH(thin_dw_kernel<32>, (unsigned)blocks, 256, smem, st, X, ldx, dZ, dW, db, M, (int)K, (int)N, rows);
+  B200RL_CHECK_LAUNCH("thin_dw");
+  return B200RL_OK;
+}
+
 int b200rl_set_gemm_mode(int mode) {
   B200RL_CHECK_ARG(mode >= 0 && mode <= 2, "gemm mode must be 0 (fp32 FFMA), 1 (tcgen05 3xTF32) "
                                            "or 2 (tcgen05 1xTF32)");
@@ -1152,6 +1353,8 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
   if (skinny_ok(M, K, N))
     return SKINNY_BY_N(skinny_fwd_launch, N, X, ldx ? ldx : K, W, bias, Y, M, K, N, act,
                        (cudaStream_t)stream);
+  if (thin_ok(X, ldx, W, M, K, N) && al16(Y) && (bias == nullptr || al16(bias)))
+    return thin_fwd_launch(X, ldx ? ldx : K, W, bias, Y, M, K, N, act, (cudaStream_t)stream);
   GemmArgs g{Y, bias, M, N, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
   return launch_gemm(ARow{X, ldx ? ldx : K}, BRow{W, N}, g);
 }
@@ -1187,7 +1390,11 @@ int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* d
     if (rc) return rc;
   }
   bool db_fused = false;
-  if (dW) {
+  if (dW && thin_ok(X, ldx, W, M, K, N) && al16(dY)) {
+    rc = thin_dw_launch(X, ldx ? ldx : K, dY, dW, db, M, K, N, accumulate, st);
+    if (rc) return rc;
+    db_fused = true;
+  } else if (dW) {
     GemmArgs g{dW, nullptr, K, N, M, B200RL_ACT_NONE, accumulate, workspace, ws_bytes, st};
     rc = launch_grad_gemm(ACol{X, ldx ? ldx : K}, BRow{dY, N}, g, db, &db_fused);
     if (rc) return rc;

@@ -10,16 +10,19 @@
 // prologue (TMEM allocation, barrier init) and the epilogue exposed on every tile.  Here:
 //
 //   * one CTA per SM, persistent over (split, m-tile, n-tile) work items;
-//   * warps 0-3   LOADERS: cp.async (LDGSTS, 16 B, zero-fill) of the raw operand chunks straight
+//   * warps 0-7   LOADERS: cp.async (LDGSTS, 16 B, zero-fill) of the raw operand chunks straight
 //                 into their final 128B-swizzled position of a deep stage ring; completion is
 //                 signalled with cp.async.mbarrier.arrive.noinc, so the loader never waits for
-//                 data and runs ahead by the full ring;
-//   * warps 4-7   CONVERTERS: shared -> shared; split every fp32 chunk into its TF32 hi plane
-//                 (in place) and lo plane, or expand raw uint8 pixels to fp32; linear,
+//                 data and runs ahead by the full ring; plain row-major 2-D operands are one
+//                 cp.async.bulk.tensor (TMA) per tile instead;
+//   * warps 8-15  CONVERTERS: shared -> shared; compute the TF32 lo plane of every fp32 chunk
+//                 (the raw tile is the hi plane), or expand raw uint8 pixels to fp32; linear,
 //                 conflict-free addressing, no global address arithmetic; they also accumulate
 //                 the fused bias gradient (column sums of B) of weight-gradient GEMMs;
-//   * warp 8      one thread issues tcgen05.mma into one of TWO TMEM accumulators;
-//   * warps 9-16  EPILOGUE of tile i (tcgen05.ld, bias/activation/act' mask, stores, split-K
+//   * warp 16     one thread issues tcgen05.mma into one of TWO TMEM accumulators; the hi and lo
+//                 planes of B form one operand of N = 2 BN columns (Layout::kWide), so a 3xTF32
+//                 K step is 2 MMAs and an exact-A (uint8) step is 1;
+//   * warps 17+   EPILOGUE of tile i (tcgen05.ld, bias/activation/act' mask, stores, split-K
 //                 red.add, fused col2im scatter-add) overlaps the main loop of tile i+1;
 //   * every loop that is not a fixed 4-8x unroll is rolled, the scalar fall-back paths live in
 //                 tc_gemm.cuh (the host dispatch only sends 16-byte-vectorisable views here).
@@ -27,6 +30,8 @@
 // Shared-memory operand layouts, descriptors and the 3xTF32 scheme are those of tc_gemm.cuh.
 #pragma once
 #include <cuda.h>
+
+#include <type_traits>
 
 #include "tc_gemm.cuh"
 
@@ -44,17 +49,29 @@ using tc::mbar_init;
 using tc::mbar_wait;
 using tc::smem_addr;
 
-constexpr int kLoaderThreads = 128;
-constexpr int kConvThreads = 128;
-constexpr int kMmaWarp = 8;
-constexpr int kFirstEpiWarp = 9;
-constexpr int kEpiWarps = 8;          // two per TMEM lane quadrant, each drains half of the columns
+// Run-7 trace: once the MMA count per K step dropped (WIDE below), the K-block period (620-720 ns)
+// stayed above every role's busy time (loaders ~400-500, converters ~350-450, MMA issue ~230-410):
+// a loader and a converter warp share each scheduler and both are chains of dependent scalar
+// instructions (address arithmetic -> LDGSTS; LDS -> split -> STS), i.e. latency- not
+// throughput-bound.  Two warps per role per scheduler hide that latency.
+constexpr int kLoaderThreads = 256;
+constexpr int kConvThreads = 256;
+constexpr int kMmaWarp = (kLoaderThreads + kConvThreads) / 32;
+constexpr int kFirstEpiWarp = kMmaWarp + 1;
+// Epilogue warps: 8 are launched; `epi_warps` (4 or 8, per launch) of them work, the others park
+// on the closing barrier.  Run 8: with 8 working warps (two per TMEM lane quadrant, each draining
+// half of the columns) the epilogue-bound GEMMs (col2im scatter, K <= ~200) are 5-35 % faster,
+// the main-loop-bound ones 2-5 % slower (eight more warps polling accumulator barriers).
+constexpr int kEpiWarps = 8;
 constexpr int kThreads = (kFirstEpiWarp + kEpiWarps) * 32;
+static_assert(kLoaderThreads == 256 && kConvThreads == 256, "thread -> chunk maps below assume 256");
 
 // The tensor core ignores the low 13 mantissa bits of a TF32 operand, so the raw fp32 tile IS the
 // hi plane and only the lo plane is computed (x - (x & 0xFFFFE000)); measured bit-identical to
 // the explicitly masked hi plane on every layer (profiles/r2/run2_tc2_check*.jsonl).
 // bit 0 of the flags: store the masked hi plane anyway (A/B switch for tests/profiles).
+// bits 3/4/5: ABLATIONS for profiles/tc2_ablate.py (results are garbage, only the time is read):
+// loaders issue no copies / converters do no work / the MMA thread issues no MMAs.
 __device__ int g_tc2_flags = 0;
 // optional pipeline trace (b200rl_tc2_trace_buffer): CTA 0 stamps %globaltimer at the start and end
 // of every pipeline step of each role: trace[role][step][2], role 0 loader / 1 converter / 2 MMA /
@@ -69,6 +86,9 @@ __device__ __forceinline__ void trace(long long* tr, int role, uint32_t step, in
   }
 }
 
+#ifndef B200RL_TC2_WIDE_MAX_BN
+#define B200RL_TC2_WIDE_MAX_BN 128
+#endif
 template <int BN, int PASSES, bool A_EXACT>
 struct Layout {
   static constexpr int kATile = kBM * 128;
@@ -79,6 +99,13 @@ struct Layout {
   static constexpr int kStage = kNumA * kATile + kNumB * kBTile + kRawA;
   static constexpr int kBudget = 196 * 1024;
   static constexpr int kStages = (kBudget / kStage) > 8 ? 8 : (kBudget / kStage);
+  // WIDE: the hi and lo planes of B sit side by side as ONE 2*BN-column operand, so that
+  // A_hi x [B_hi | B_lo] is a single MMA of N = 2 BN into two accumulator column sets which the
+  // epilogue adds.  The run-5 trace shows ~90 cycles per 128 x N x 8 TF32 MMA for N = 32, 64 and
+  // 128 alike (the instruction is bound by its A-operand read / fixed latency, not by N), so a
+  // 3xTF32 K step costs 2 MMAs instead of 3 and an exact-A step 1 instead of 2.
+  static constexpr bool kWide = PASSES == 3 && BN <= B200RL_TC2_WIDE_MAX_BN;
+  static constexpr int kAccCols = kWide ? 2 * BN : BN;     // TMEM columns of one accumulator
   static constexpr int kBarBytes = 512;
   static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + kBarBytes + BN * 4;
   static_assert(kStage % 1024 == 0, "stage planes must stay 1024 B aligned");
@@ -105,16 +132,44 @@ __device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
                "f"(v.z), "f"(v.w)
                : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
+        "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 // one out-of-line body instead of 16 inlined tanhf expansions per epilogue step
 __device__ __noinline__ float act_tanh(float x) { return tanhf(x); }
 __device__ __forceinline__ float tf32_hi(float x) {
   return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
 }
 
-// Waits of roles that have slack (loaders waiting for a free stage, the epilogue waiting for the
-// next accumulator): poll a few times, then sleep between polls so that the spinning warps do not
-// take issue slots from the converter / MMA warps of the same scheduler.
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+// Run-10 ncu source page of conv1.fwd: 2850 warp instructions per K block per CTA (70 % of the
+// four schedulers' issue slots), of which a quarter were mbarrier polls (test_wait spins of the
+// converters, nanosleep polls of the eight epilogue warps).  mbarrier.try_wait suspends the warp in
+// hardware until the phase flips (or a time limit passes), so waiting roles stop taking issue slots
+// from the loader / converter warps of their scheduler.  bit 6 of the flags: poll with test_wait
+// as before (A/B switch).
+__device__ __forceinline__ void mbar_wait_hw(uint32_t bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, bool poll) {
+  if (!poll) {
+    mbar_wait_hw(bar, parity);
+    return;
+  }
   uint32_t done;
   int polls = 0;
   do {
@@ -127,6 +182,10 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
         : "memory");
     if (!done && ++polls > 4) __nanosleep(64);
   } while (!done);
+}
+__device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity, bool poll) {
+  if (poll) mbar_wait(bar, parity);
+  else mbar_wait_hw(bar, parity);
 }
 
 struct Work {
@@ -153,11 +212,12 @@ __device__ __forceinline__ Work decode_work(int64_t w, int64_t tiles_m, int64_t 
 
 // ---- loaders ------------------------------------------------------------------------------------
 // K-contiguous fp32 view, ROWS x 32 tile: thread t owns chunk j = t & 7 (4 consecutive k) of rows
-// (t >> 3) + 16 i.  sw128(r0 + 16 i, j) = sw128(r0, j) + 2048 i.  Row base POINTERS are hoisted per
+// (t >> 3) + 32 i.  sw128(r0 + 32 i, j) = sw128(r0, j) + 4096 i.  Row base POINTERS are hoisted per
 // tile; a K block costs one k_off and, per chunk, one 64-bit add + the LDGSTS.
 template <int ROWS, class V>
 struct LoadKContigF32 {
-  static constexpr int NR = ROWS / 16;
+  static constexpr int RPP = kLoaderThreads / 8;   // rows per pass
+  static constexpr int NR = ROWS / RPP;
   const char* rowp[NR];                            // element (row, 0); rows past the edge: row 0
   uint32_t ok, dst0;
   int j;
@@ -168,7 +228,7 @@ struct LoadKContigF32 {
     ok = 0;
 #pragma unroll
     for (int i = 0; i < NR; ++i) {
-      const int64_t r = row0 + r0 + 16 * i;
+      const int64_t r = row0 + r0 + RPP * i;
       const bool in = r < row_limit;
       rowp[i] = reinterpret_cast<const char*>(v.addr(in ? v.row_off(r) : 0));
       ok |= (in ? 1u : 0u) << i;
@@ -180,7 +240,7 @@ struct LoadKContigF32 {
     const int64_t kbytes = kin ? v.k_off(k) * (int64_t)sizeof(float) : 0;
 #pragma unroll
     for (int i = 0; i < NR; ++i)
-      cp_async16(plane + dst0 + 2048u * i, rowp[i] + kbytes, (kin && ((ok >> i) & 1u)) ? 16u : 0u);
+      cp_async16(plane + dst0 + (RPP * 128u) * i, rowp[i] + kbytes, (kin && ((ok >> i) & 1u)) ? 16u : 0u);
   }
 };
 
@@ -189,8 +249,8 @@ struct LoadKContigF32 {
 // its chunks are fixed for the whole kernel.  Linear views (k_off = k * ld) step their pointer;
 // the conv filter-gradient view needs a full (n, oy, ox) decode per k: lane l computes it for
 // k0 + l once and the offsets are fetched by shuffle.
-template <int ROWS, class V>
-struct LoadMnF32 {
+template <int ROWS, class V, int LROWS = ROWS>
+struct LoadMnF32 {                                 // LROWS: rows of the shared-memory tile layout
   static constexpr int CPR = ROWS / 4;
   static constexpr int KSTEP = kLoaderThreads / CPR;
   static constexpr int NC = 32 / KSTEP;            // chunks per thread
@@ -205,7 +265,7 @@ struct LoadMnF32 {
     ok = r < row_limit;                            // rows % 4 == 0 (host check)
     rowp = reinterpret_cast<const char*>(v.addr(ok ? v.row_off(r) : 0));
 #pragma unroll
-    for (int i = 0; i < NC; ++i) dst[i] = tc::mn128<ROWS>((uint32_t)cm, (uint32_t)(kk0 + KSTEP * i));
+    for (int i = 0; i < NC; ++i) dst[i] = tc::mn128<LROWS>((uint32_t)cm, (uint32_t)(kk0 + KSTEP * i));
   }
   __device__ __forceinline__ void issue(const V& v, uint32_t plane, int64_t k0, int64_t ke) {
     if constexpr (V::kLinearK) {
@@ -230,35 +290,34 @@ struct LoadMnF32 {
   }
 };
 
-// K-contiguous uint8 im2col view (conv1 forward): raw tile [128 rows][32 B]; thread t copies the
-// two 16-byte halves of row t (one ky row of the patch = 32 contiguous bytes).  The halves of rows
-// with bit 2 set are swapped so that the converter's 16-byte reads are bank-conflict free.
+// K-contiguous uint8 im2col view (conv1 forward): raw tile [128 rows][32 B]; thread t copies
+// 16-byte half t & 1 of row t >> 1 (one ky row of the patch = 32 contiguous bytes).  The halves of
+// rows with bit 2 set are swapped (kept from the 128-thread converter; harmless).
 template <class V>
 struct LoadKContigU8 {
   int64_t roff;
   bool ok;
-  uint32_t dst[2];
+  uint32_t dst;
+  int h;
   __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
-    const int64_t r = row0 + t;
+    const int row = t >> 1;
+    h = t & 1;
+    const int64_t r = row0 + row;
     ok = r < row_limit;
     roff = ok ? v.row_off(r) : 0;
-    const uint32_t sw = (uint32_t)(t >> 2) & 1u;
-    dst[0] = (uint32_t)t * 32u + ((0u ^ sw) << 4);
-    dst[1] = (uint32_t)t * 32u + ((1u ^ sw) << 4);
+    const uint32_t sw = (uint32_t)(row >> 2) & 1u;
+    dst = (uint32_t)row * 32u + (((uint32_t)h ^ sw) << 4);
   }
   __device__ __forceinline__ void issue(const V& v, uint32_t raw, int64_t k0, int64_t ke) {
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int64_t k = k0 + 16 * h;
-      const bool in = ok && k < ke;                // K % 16 == 0 (host check)
-      cp_async16(raw + dst[h], v.addr(in ? roff + v.k_off(k) : 0), in ? 16u : 0u);
-    }
+    const int64_t k = k0 + 16 * h;
+    const bool in = ok && k < ke;                  // K % 16 == 0 (host check)
+    cp_async16(raw + dst, v.addr(in ? roff + v.k_off(k) : 0), in ? 16u : 0u);
   }
 };
 
 // MN-major uint8 view (conv1 filter gradient): raw tile [32 k][128 B]; the 128 patch indices of a
 // k-row are 128/(KW*C) ky segments of contiguous bytes; thread t copies 16-byte chunk c = t & 7 of
-// k-rows (t >> 3) and (t >> 3) + 16.
+// k-row t >> 3.
 template <class V>
 struct LoadMnU8 {
   int64_t roff;
@@ -274,15 +333,12 @@ struct LoadMnU8 {
   __device__ __forceinline__ void issue(const V& v, uint32_t raw, int64_t k0, int64_t ke) {
     const int lane = threadIdx.x & 31;
     const int64_t my_koff = (k0 + lane < ke) ? v.k_off(k0 + lane) : 0;
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const int kk = kk0 + 16 * i;
-      const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
-      const bool in = ok && (k0 + kk < ke);
-      // slot c ^ 2(kk & 3): see convert_u8_mn
-      cp_async16(raw + (uint32_t)kk * 128u + (((uint32_t)c ^ (((uint32_t)kk & 3u) << 1)) << 4),
-                 v.addr(in ? roff + koff : 0), in ? 16u : 0u);
-    }
+    const int kk = kk0;
+    const int64_t koff = __shfl_sync(0xffffffffu, my_koff, kk);
+    const bool in = ok && (k0 + kk < ke);
+    // slot c ^ 2(kk & 3): see convert_u8_mn
+    cp_async16(raw + (uint32_t)kk * 128u + (((uint32_t)c ^ (((uint32_t)kk & 3u) << 1)) << 4),
+               v.addr(in ? roff + koff : 0), in ? 16u : 0u);
   }
 };
 
@@ -335,6 +391,22 @@ __device__ __forceinline__ void convert_f32(uint32_t plane, uint32_t lo_off, int
     if (do_colsum) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
   }
 }
+// MN-major B tile of the WIDE layout: per 4-row k atom, the BN/32 hi atoms are followed by the
+// BN/32 lo atoms (mn128<2 BN> with the lo rows at cm + BN/4), i.e. lo = hi + BN * 16 bytes.
+template <int BN>
+__device__ __forceinline__ void convert_f32_mn_wide(uint32_t plane, int t, bool raw_hi,
+                                                    float4& colsum, bool do_colsum) {
+#pragma unroll 4
+  for (int i = t; i < BN * 8; i += kConvThreads) {
+    const uint32_t off = (uint32_t)(i / BN) * (2u * BN * 16u) + (uint32_t)(i % BN) * 16u;
+    const float4 v = lds128(plane + off);
+    float4 h;
+    h.x = tf32_hi(v.x); h.y = tf32_hi(v.y); h.z = tf32_hi(v.z); h.w = tf32_hi(v.w);
+    if (!raw_hi) sts128(plane + off, h);
+    sts128(plane + off + BN * 16u, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+    if (do_colsum) { colsum.x += v.x; colsum.y += v.y; colsum.z += v.z; colsum.w += v.w; }
+  }
+}
 // 4 packed uint8 -> 4 floats, exactly: PRMT builds 0x4B0000bb = 2^23 + b, one FADD removes the
 // 2^23 (2 full-rate instructions per pixel instead of shift + mask + I2F)
 __device__ __forceinline__ void u8x4_to_f32(uint32_t w, float4& o) {
@@ -343,23 +415,22 @@ __device__ __forceinline__ void u8x4_to_f32(uint32_t w, float4& o) {
   o.z = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7542)) - 8388608.f;
   o.w = __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7543)) - 8388608.f;
 }
-// raw [128 rows][32 B] uint8 -> K-major SWIZZLE_128B fp32 tile: thread t expands row t
+// raw [128 rows][32 B] uint8 -> K-major SWIZZLE_128B fp32 tile: thread t expands 16-byte half
+// t & 1 of row t >> 1 (a quarter-warp stores 4 rows x chunks {q, q + 4}: eight distinct slots)
 __device__ __forceinline__ void convert_u8_kcontig(uint32_t raw, uint32_t plane, int t) {
-  const uint32_t sw = (uint32_t)(t >> 2) & 1u;
+  const uint32_t row = (uint32_t)t >> 1, h = (uint32_t)t & 1u;
+  const uint32_t sw = (row >> 2) & 1u;
+  uint4 p;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
+               : "r"(raw + row * 32u + ((h ^ sw) << 4))
+               : "memory");
+  const uint32_t w[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    uint4 p;
-    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
-                 : "r"(raw + (uint32_t)t * 32u + (((uint32_t)h ^ sw) << 4))
-                 : "memory");
-    const uint32_t w[4] = {p.x, p.y, p.z, p.w};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float4 o;
-      u8x4_to_f32(w[q], o);
-      sts128(plane + tc::sw128((uint32_t)t, (uint32_t)(4 * h + q)), o);
-    }
+  for (int q = 0; q < 4; ++q) {
+    float4 o;
+    u8x4_to_f32(w[q], o);
+    sts128(plane + tc::sw128(row, 4u * h + (uint32_t)q), o);
   }
 }
 // raw [32 k][128 B] uint8 -> MN-major fp32 tile (128 rows).  Chunk (kk, c) = the 16 patch
@@ -370,10 +441,9 @@ __device__ __forceinline__ void convert_u8_kcontig(uint32_t raw, uint32_t plane,
 // slots of one 512 B atom of the SWIZZLE_128B_BASE32B layout -- no bank conflicts on either side.
 __device__ __forceinline__ void convert_u8_mn(uint32_t raw, uint32_t plane, int t) {
   const uint32_t kin = (uint32_t)t & 3u, cb = ((uint32_t)t >> 2) & 1u;
-  const uint32_t c = ((((uint32_t)t >> 3) & 3u) << 1) | cb, kq = ((uint32_t)t >> 5) & 3u;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const uint32_t kk = ((kq + 4u * i) << 2) | kin;
+  const uint32_t c = ((((uint32_t)t >> 3) & 3u) << 1) | cb, kq = ((uint32_t)t >> 5) & 7u;
+  {
+    const uint32_t kk = (kq << 2) | kin;
     uint4 p;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                  : "=r"(p.x), "=r"(p.y), "=r"(p.z), "=r"(p.w)
@@ -397,7 +467,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     tc2_gemm_kernel(const AL a, const BL b, const EpiArgs epi, float* __restrict__ C,
                     const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int act,
                     int beta, int splits, int64_t k_per_split, float* __restrict__ ws,
-                    float out_scale, int64_t tiles_m, int64_t tiles_n,
+                    float out_scale, int64_t tiles_m, int64_t tiles_n, int epi_warps,
                     const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB) {
   using L = Layout<BN, PASSES, AL::kExact>;
@@ -426,12 +496,13 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_addr(&acc_full[i]), 1);
-      mbar_init(smem_addr(&acc_empty[i]), kEpiWarps);
+      mbar_init(smem_addr(&acc_empty[i]), (uint32_t)epi_warps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < BN) scol[tid] = 0.f;
-  constexpr int kCols = 2 * BN;                    // two accumulators; power of two >= 64
+  constexpr bool kWide = L::kWide;
+  constexpr int kCols = 2 * L::kAccCols;           // two accumulators; power of two >= 64
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_addr(tmem_slot)),
@@ -446,18 +517,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int64_t total = tiles_m * tiles_n * (int64_t)splits;
   long long* const tr = blockIdx.x == 0 ? g_tc2_trace : nullptr;
+  const bool poll = (g_tc2_flags & 64) != 0;
   constexpr bool kLoA = PASSES == 3 && !AL::kExact;
   constexpr bool kLoB = PASSES == 3;
   constexpr uint32_t kOffB = L::kNumA * L::kATile;
   constexpr uint32_t kOffRaw = kOffB + L::kNumB * L::kBTile;
 
-  if (warp < 4) {
+  if (warp < kLoaderThreads / 32) {
     // ======================= loaders =======================
     typename LoaderFor<kBM, AL>::type la;
-    typename LoaderFor<BN, BL>::type lb;
+    typename std::conditional<kWide && !BL::kKContig, LoadMnF32<BN, BL, 2 * BN>,
+                              typename LoaderFor<BN, BL>::type>::type lb;
     LoadTma2D<kBM> ta;                             // used instead of la / lb for plain 2-D operands
     LoadTma2D<BN> tb;
     const bool use_tma = (g_tc2_flags & 4) == 0;   // bit 2: cp.async loaders for those as well (A/B)
+    const bool no_load = (g_tc2_flags & 8) != 0;
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
@@ -468,23 +542,26 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
-        mbar_wait_relaxed(smem_addr(&empty[s]), ph ^ 1u);
+        mbar_wait_relaxed(smem_addr(&empty[s]), ph ^ 1u, poll);
         if (tid == 0) trace(tr, 0, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         const int64_t k0 = wk.kb + (int64_t)kbi * kBK;
         const uint32_t bar = smem_addr(&raw_full[s]);
-        if (AL::kTma2D && use_tma) ta.issue(&tmA, st, k0, bar);
-        else la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
-        if (BL::kTma2D && use_tma) tb.issue(&tmB, st + kOffB, k0, bar);
-        else lb.issue(b, st + kOffB, k0, wk.ke);
+        if (!no_load) {
+          if (AL::kTma2D && use_tma) ta.issue(&tmA, st, k0, bar);
+          else la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
+          if (BL::kTma2D && use_tma) tb.issue(&tmB, st + kOffB, k0, bar);
+          else lb.issue(b, st + kOffB, k0, wk.ke);
+        }
         cp_async_arrive(smem_addr(&raw_full[s]));
         if (tid == 0) trace(tr, 0, it, 1);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kMmaWarp) {
     // ======================= converters =======================
     const int t = tid - kLoaderThreads;
     const bool raw_hi = (g_tc2_flags & 1) == 0;
+    const bool no_conv = (g_tc2_flags & 16) != 0;
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
@@ -493,17 +570,21 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1u;
-        mbar_wait(smem_addr(&raw_full[s]), ph);
+        mbar_wait_tight(smem_addr(&raw_full[s]), ph, poll);
         if (t == 0) trace(tr, 1, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         float4 none = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (AL::kExact) {
+        if (no_conv) {
+        } else if (AL::kExact) {
           if (AL::kKContig) convert_u8_kcontig(st + kOffRaw, st, t);
           else convert_u8_mn(st + kOffRaw, st, t);
         } else if (PASSES == 3 || !raw_hi) {
           convert_f32<kLoA>(st, L::kATile, L::kATile, t, raw_hi, none, false);
         }
-        if (PASSES == 3 || !raw_hi || do_colsum)
+        if (no_conv) {
+        } else if (kWide && !BL::kKContig)
+          convert_f32_mn_wide<BN>(st + kOffB, t, raw_hi, csum, do_colsum);
+        else if (PASSES == 3 || !raw_hi || do_colsum)
           convert_f32<kLoB>(st + kOffB, L::kBTile, L::kBTile, t, raw_hi, csum, do_colsum);
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_addr(&conv_full[s]));
@@ -520,42 +601,45 @@ __global__ void __launch_bounds__(kThreads, 1)
         atomicAdd(&scol[4 * cm + 1], csum.y);
         atomicAdd(&scol[4 * cm + 2], csum.z);
         atomicAdd(&scol[4 * cm + 3], csum.w);
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(kConvThreads) : "memory");
         if (t < BN) {
           const float v = scol[t];
           scol[t] = 0.f;
           if (wk.n0 + t < N) atomicAdd(epi.colsum + wk.n0 + t, v);
         }
-        asm volatile("bar.sync 2, 128;" ::: "memory");
+        asm volatile("bar.sync 2, %0;" ::"n"(kConvThreads) : "memory");
       }
     }
   } else if (warp == kMmaWarp) {
     // ======================= MMA issuer =======================
     if (lane == 0) {
       constexpr uint32_t idesc = tc::make_idesc(BN, !AL::kKContig, !BL::kKContig);
+      constexpr uint32_t idesc_w = tc::make_idesc(2 * BN, !AL::kKContig, !BL::kKContig);
+      constexpr int kBRows = kWide ? 2 * BN : BN;   // rows of the MN-major B tile layout
       // One thread issues every MMA, so its scalar instruction stream IS the K-loop rate once the
       // operands arrive (run 4 trace: 560 ns per K block, ~30 instructions per MMA, most of them
       // rebuilding shared-memory descriptors).  Everything but the 14-bit start-address field of a
       // descriptor is constant: keep the constants, and advance the start fields (16-byte units)
       // with 32-bit adds.
       constexpr uint32_t kaStep = AL::kKContig ? 2u : (2u * (kBM / 32) * 512u) >> 4;   // per K = 8
-      constexpr uint32_t kbStep = BL::kKContig ? 2u : (2u * (BN / 32) * 512u) >> 4;
+      constexpr uint32_t kbStep = BL::kKContig ? 2u : (2u * (kBRows / 32) * 512u) >> 4;
       constexpr uint32_t kStageStep = (uint32_t)L::kStage >> 4;
       const uint64_t dA = AL::kKContig ? tc::make_desc(0) : tc::make_desc_mn(0, (kBM / 32) * 512u);
-      const uint64_t dB = BL::kKContig ? tc::make_desc(0) : tc::make_desc_mn(0, (BN / 32) * 512u);
+      const uint64_t dB = BL::kKContig ? tc::make_desc(0) : tc::make_desc_mn(0, (kBRows / 32) * 512u);
       const uint32_t fa_hi = smem_base >> 4, fa_lo = (smem_base + L::kATile) >> 4;
       const uint32_t fb_hi = (smem_base + kOffB) >> 4, fb_lo = (smem_base + kOffB + L::kBTile) >> 4;
+      const bool no_mma = (g_tc2_flags & 32) != 0;
       uint32_t it = 0, tl = 0;
       for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
         const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
         const uint32_t buf = tl & 1u;
-        mbar_wait(smem_addr(&acc_empty[buf]), ((tl >> 1) & 1u) ^ 1u);
+        mbar_wait_tight(smem_addr(&acc_empty[buf]), ((tl >> 1) & 1u) ^ 1u, poll);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tmem_d = tmem_base + buf * BN;
+        const uint32_t tmem_d = tmem_base + buf * L::kAccCols;
 #pragma unroll 1
         for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1u;
-          mbar_wait(smem_addr(&conv_full[s]), ph);
+          mbar_wait_tight(smem_addr(&conv_full[s]), ph, poll);
           trace(tr, 2, it, 0);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -563,9 +647,16 @@ __global__ void __launch_bounds__(kThreads, 1)
           const uint32_t first = kbi == 0 ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < kBK / 8; ++ks) {
+            if (no_mma) break;
             const uint32_t oa = so + (uint32_t)ks * kaStep, ob = so + (uint32_t)ks * kbStep;
             const uint32_t acc0 = ks == 0 ? first : 1u;
-            if (PASSES == 3 && AL::kExact) {
+            if (kWide && AL::kExact) {
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc_w, acc0);
+            } else if (kWide) {
+              // columns [0, BN): A_hi B_hi + A_lo B_hi; columns [BN, 2 BN): A_hi B_lo
+              tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc_w, acc0);
+              tc::tc_mma_tf32(tmem_d, dA + (fa_lo + oa), dB + (fb_hi + ob), idesc, 1u);
+            } else if (PASSES == 3 && AL::kExact) {
               tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_lo + ob), idesc, acc0);
               tc::tc_mma_tf32(tmem_d, dA + (fa_hi + oa), dB + (fb_hi + ob), idesc, 1u);
             } else if (PASSES == 3) {
@@ -583,21 +674,23 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < kFirstEpiWarp + epi_warps) {
     // ======================= epilogue =======================
     const int q = warp & 3;                        // TMEM lane quadrant this warp may read
-    const int chalf = (warp - kFirstEpiWarp) >> 2; // which half of the tile's columns it drains
+    const int chalf = (warp - kFirstEpiWarp) >> 2; // which part of the tile's columns it drains
+    const int kColsPerWarp = BN / (epi_warps >> 2);
     uint32_t tl = 0;
     for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
       const uint32_t buf = tl & 1u;
-      mbar_wait_relaxed(smem_addr(&acc_full[buf]), (tl >> 1) & 1u);
+      mbar_wait_relaxed(smem_addr(&acc_full[buf]), (tl >> 1) & 1u, poll);
       if (warp == kFirstEpiWarp && lane == 0) trace(tr, 3, tl, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t m = wk.m0 + q * 32 + lane;
       float* out = (splits > 1 && EPI == EPI_STORE) ? ws + (int64_t)wk.split * M * N : C;
       const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
       const bool final_pass = splits == 1;
+      const bool vec_mask = (N & 3) == 0 && (epi.mask.ld & 3) == 0 && ((uintptr_t)epi.mask.y & 15) == 0;
       // col2im destination of this row (EPI_COL2IM): pos -> (n, oy, ox)
       float* cbase = nullptr;
       const float* ybase = nullptr;
@@ -612,17 +705,21 @@ __global__ void __launch_bounds__(kThreads, 1)
         if (epi.mask.y) ybase = epi.mask.y + (int64_t)img * epi.mask.ld + in_off;
       }
 #pragma unroll 1
-      for (int c = chalf * (BN / 2); c < (chalf + 1) * (BN / 2); c += 16) {
+      for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 16) {
         uint32_t r[16];
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + (uint32_t)c;
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-            "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
-              "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
-              "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-            : "r"(taddr));
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const uint32_t taddr =
+            tmem_base + ((uint32_t)(q * 32) << 16) + buf * L::kAccCols + (uint32_t)c;
+        tmem_ld16(taddr, r);
+        if (kWide) {
+          uint32_t r2[16];
+          tmem_ld16(taddr + BN, r2);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+        } else {
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        }
         const int64_t nb = wk.n0 + c;
         if (m >= M || nb >= N) continue;
         if (EPI == EPI_COL2IM) {
@@ -685,9 +782,22 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             if (epi.mask.y) {
               const float* yp = epi.mask.y + m * epi.mask.ld + nb;
+              if (vec_mask) {                      // 4 x LDG.128 instead of 16 scalar loads per lane
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (full || nb + j < N) v[j] = dact(yp[j], v[j], epi.mask.act);
+                for (int j = 0; j < 16; j += 4) {
+                  if (nb + j < N) {
+                    const float4 y = *reinterpret_cast<const float4*>(yp + j);
+                    v[j] = dact(y.x, v[j], epi.mask.act);
+                    v[j + 1] = dact(y.y, v[j + 1], epi.mask.act);
+                    v[j + 2] = dact(y.z, v[j + 2], epi.mask.act);
+                    v[j + 3] = dact(y.w, v[j + 3], epi.mask.act);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                  if (full || nb + j < N) v[j] = dact(yp[j], v[j], epi.mask.act);
+              }
             }
             if (beta) {
 #pragma unroll

@@ -273,6 +273,9 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip configs 1/3/4/5 and dp_parity')
+  ap.add_argument('--ncu-step', action='store_true',
+                  help='after warm-up run ONE un-captured step between cudaProfilerStart/Stop and '
+                       'exit (target of `ncu --profile-from-start off`; prints no bench value)')
   args = ap.parse_args()
   if args.impl == 'reference':
     return run_reference(args)
@@ -418,6 +421,14 @@ def main():
   for _ in range(W):
     fn()
   sync_all()
+  if args.ncu_step:
+    torch.cuda.cudart().cudaProfilerStart()
+    step()
+    torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
+    if rank == 0:
+      print(json.dumps({'ncu_step': True, 'launches_per_step': launches_per_step}))
+    return
 
   # ---- timed region: R blocks of K steps, CUDA events, max over ranks, median block -------------
   clocks = ClockSampler(local_rank)

@@ -53,7 +53,8 @@ const char* b200rl_last_error(void);
 int b200rl_version(void);
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t b200rl_launch_count(void);
-/* Programmatic dependent launch: when enabled (or B200RL_PDL=1 in the environment) every kernel
+/* Programmatic dependent launch: when enabled (the default; B200RL_PDL=0 in the environment or
+ * b200rl_set_pdl(0) switches it off) every kernel
  * is launched with cudaLaunchAttributeProgrammaticStreamSerialization, so inside a captured step
  * (common.function, utils/common.py:128 in the reference) the next node's launch overlaps the
  * running one; every kernel orders itself with griddepcontrol.wait. */

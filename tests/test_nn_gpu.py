@@ -42,7 +42,7 @@ def _net_and_oracle(cuda, layers, input_shape, in_dtype=torch.float32):
 @pytest.mark.parametrize('M,K,N,act', [
     (1, 4, 2, None), (64, 4, 100, 'relu'), (256, 100, 2, None), (256, 3136, 512, 'relu'),
     (256, 512, 6, None), (4096, 17, 200, 'tanh'), (1000, 200, 100, 'tanh'), (33, 65, 129, 'relu'),
-    (5000, 23, 256, 'relu')])
+    (5000, 23, 256, 'relu'), (37, 32, 20, None), (300, 8, 64, 'relu'), (70001, 17, 200, 'tanh')])
 def test_dense_fwd_bwd(cuda, M, K, N, act):
   rng = np.random.RandomState(M + K + N)
   net, orc = _net_and_oracle(cuda, [L.Dense(N, activation=act)], (K,))
