@@ -619,13 +619,29 @@ __global__ void __launch_bounds__(256) skinny_dw_kernel(const float* __restrict_
       }
     }
   }
+  if (G > 1) {
+    // the row groups add their sums in a fixed order (a single-CTA launch stays bit-reproducible)
+    extern __shared__ float skinny_red[];             // [K, N]
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) skinny_red[i] = 0.f;
+    for (int g = 0; g < G; ++g) {
+      __syncthreads();
+      if (live && rg == g && kt < K) {
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) {
-    const int k = kt + j * blockDim.x;
-    if (k < K && live) {
+        for (int n = 0; n < NMAX; ++n)
+          if (n < N) skinny_red[kt * N + n] += acc[0][n];
+      }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < K * N; i += blockDim.x) atomicAdd(dW + i, skinny_red[i]);
+  } else {
 #pragma unroll
-      for (int n = 0; n < NMAX; ++n)
-        if (n < N) atomicAdd(dW + (int64_t)k * N + n, acc[j][n]);
+    for (int j = 0; j < KPT; ++j) {
+      const int k = kt + j * blockDim.x;
+      if (k < K && live) {
+#pragma unroll
+        for (int n = 0; n < NMAX; ++n)
+          if (n < N) atomicAdd(dW + (int64_t)k * N + n, acc[j][n]);
+      }
     }
   }
   if (db != nullptr && (int)threadIdx.x < N) atomicAdd(db + threadIdx.x, bsum);
@@ -699,7 +715,7 @@ __global__ void __launch_bounds__(256) thin_fwd_kernel(const float* __restrict__
 
 // dW[K,N] += X^T dZ, db[N] += column sums of dZ over the CTA's row range.
 template <int KMAX>
-__global__ void __launch_bounds__(256) thin_dw_kernel(const float* __restrict__ X, int64_t ldx,
+__global__ void __launch_bounds__(256, KMAX <= 20 ? 2 : 1) thin_dw_kernel(const float* __restrict__ X, int64_t ldx,
                                                       const float* __restrict__ dZ,
                                                       float* __restrict__ dW,
                                                       float* __restrict__ db, int64_t M, int K,
@@ -725,16 +741,18 @@ __global__ void __launch_bounds__(256) thin_dw_kernel(const float* __restrict__ 
     }
     __syncthreads();
     if (!active) continue;
-    float4 dz[8];
+#pragma unroll 1
+    for (int h = 0; h < 8; h += 4) {                   // two halves of 4 rows: 128 registers, 2 CTAs / SM
+    float4 dz[4];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int64_t m = m0 + rg * 8 + r;
+    for (int r = 0; r < 4; ++r) {
+      const int64_t m = m0 + rg * 8 + h + r;
       dz[r] = m < me ? reinterpret_cast<const float4*>(dZ + m * N)[cq] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < 4; ++r) {
       bsum.x += dz[r].x; bsum.y += dz[r].y; bsum.z += dz[r].z; bsum.w += dz[r].w;
-      const float* xr = sx + (rg * 8 + r) * KMAX;
+      const float* xr = sx + (rg * 8 + h + r) * KMAX;
 #pragma unroll
       for (int k = 0; k < KMAX; k += 4) {
         const float4 x = *reinterpret_cast<const float4*>(xr + k);
@@ -748,19 +766,27 @@ __global__ void __launch_bounds__(256) thin_dw_kernel(const float* __restrict__ 
         acc[k + 3].z = fmaf(x.w, dz[r].z, acc[k + 3].z); acc[k + 3].w = fmaf(x.w, dz[r].w, acc[k + 3].w);
       }
     }
-  }
-  __syncthreads();
-  if (active) {
-#pragma unroll
-    for (int k = 0; k < KMAX; ++k) {
-      if (k < K) {
-        float* d = sred + k * N + 4 * cq;
-        atomicAdd(d + 0, acc[k].x); atomicAdd(d + 1, acc[k].y);
-        atomicAdd(d + 2, acc[k].z); atomicAdd(d + 3, acc[k].w);
-      }
     }
-    float* d = sred + K * N + 4 * cq;
-    atomicAdd(d + 0, bsum.x); atomicAdd(d + 1, bsum.y); atomicAdd(d + 2, bsum.z); atomicAdd(d + 3, bsum.w);
+  }
+  // the four row groups add their partial sums in a fixed order (a single-CTA launch, i.e. a small
+  // batch, is bit-reproducible; larger ones meet in the global atomics below)
+  for (int g = 0; g < 4; ++g) {
+    __syncthreads();
+    if (active && rg == g) {
+#pragma unroll
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          float4* d = reinterpret_cast<float4*>(sred + k * N) + cq;
+          float4 v = *d;
+          v.x += acc[k].x; v.y += acc[k].y; v.z += acc[k].z; v.w += acc[k].w;
+          *d = v;
+        }
+      }
+      float4* d = reinterpret_cast<float4*>(sred + K * N) + cq;
+      float4 v = *d;
+      v.x += bsum.x; v.y += bsum.y; v.z += bsum.z; v.w += bsum.w;
+      *d = v;
+    }
   }
   __syncthreads();
   for (int i = threadIdx.x; i < K * N; i += blockDim.x) atomicAdd(dW + i, sred[i]);
@@ -941,6 +967,19 @@ static int tc2_enabled() {
   }
   return v && !(g_tc2_host_flags & 2);
 }
+// Work distribution of the persistent GEMM: 0 = static striding (a few per cent faster when the
+// kernel has the GPU to itself), 1 = dynamic (global counter): CTAs whose SM is busy with a
+// collective or a kernel of another stream take fewer tiles instead of delaying the launch.  The
+// data-parallel Learner switches it on (run 17, 2 GPUs: 0.93 -> 0.946 weak-scaling efficiency
+// together with NCCL_MAX_CTAS=8).
+static int g_tile_sched = -1;
+static bool tile_scheduler_dynamic() {
+  if (g_tile_sched < 0) {
+    const char* e = getenv("B200RL_TILE_SCHED");
+    g_tile_sched = e ? (atoi(e) != 0) : 0;
+  }
+  return g_tile_sched != 0;
+}
 static bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 static bool tc2_ok(const ARow& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (K & 3) == 0; }
 static bool tc2_ok(const BCol& v, int64_t rows, int64_t K) { return (v.ld & 3) == 0 && al16(v.p) && (K & 3) == 0; }
@@ -1072,7 +1111,11 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   static const int epi_env = [] { const char* e = getenv("B200RL_TC2_EPI_WARPS"); return e ? atoi(e) : 0; }();
   const int epi_warps = (epi_env == 4 || epi_env == 8) ? epi_env
                         : (EPI == tc::EPI_COL2IM || kps <= 224) ? 8 : 4;
-  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, epi_warps, tmA, tmB);
+  // dynamic work distribution (b200rl_set_tile_scheduler) when a CTA has more than one item
+  static int sched_seq = 0;
+  int sched_slot = -1;
+  if (total > grid && tile_scheduler_dynamic()) sched_slot = (sched_seq++) & (tc2::kSchedSlots - 1);
+  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, epi_warps, sched_slot, tmA, tmB);
   B200RL_CHECK_LAUNCH("tc2_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
@@ -1214,7 +1257,7 @@ static int skinny_dw_launch(const float* X, int64_t ldx, const float* dY, float*
   int64_t rows = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);   // ~2 CTAs per SM; small M: 8-row slabs
   rows = (rows + 7) / 8 * 8;
   const int64_t blocks = (M + rows - 1) / rows;
-  if (K <= 256) B200RL_LAUNCH((skinny_dw_kernel<NMAX, 1>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
+  if (K <= 256) B200RL_LAUNCH((skinny_dw_kernel<NMAX, 1>), (unsigned)blocks, 256, (size_t)(K * N * sizeof(float)), st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
   else if (K <= 512) B200RL_LAUNCH((skinny_dw_kernel<NMAX, 2>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
   else B200RL_LAUNCH((skinny_dw_kernel<NMAX, 4>), (unsigned)blocks, 256, 0, st, X, ldx, dY, dW, db, M, (int)K, (int)N, rows);
   B200RL_CHECK_LAUNCH("skinny_dw");
@@ -1291,6 +1334,11 @@ int b200rl_tc2_trace_buffer(long long* dev_buf) {
   return B200RL_OK;
 }
 
+int b200rl_set_tile_scheduler(int dynamic) {
+  g_tile_sched = dynamic ? 1 : 0;
+  return B200RL_OK;
+}
+
 int b200rl_set_tc2_flags(int flags) {
   g_tc2_host_flags = flags;
   cudaError_t e = cudaMemcpyToSymbol(tc2::g_tc2_flags, &flags, sizeof(flags));
@@ -1326,7 +1374,7 @@ static int thin_dw_launch(const float* X, int64_t ldx, const float* dZ, float* d
       return B200RL_ERR_CUDA;
     }
   }
-  int64_t rows = (M + 2 * kNumSMs - 1) / (2 * kNumSMs);
+  int64_t rows = (M + 4 * kNumSMs - 1) / (4 * kNumSMs);
   rows = (rows + kThinRows - 1) / kThinRows * kThinRows;
   const int64_t blocks = (M + rows - 1) / rows;
   const int KMAX = K <= 8 ? 8 : K <= 20 ? 20 : 32;

@@ -76,6 +76,12 @@ __device__ int g_tc2_flags = 0;
 // optional pipeline trace (b200rl_tc2_trace_buffer): CTA 0 stamps %globaltimer at the start and end
 // of every pipeline step of each role: trace[role][step][2], role 0 loader / 1 converter / 2 MMA /
 // 3 epilogue (steps are K blocks for roles 0-2 and tiles for role 3), first kTraceSteps steps.
+// Dynamic tile scheduler: {next work item, finished CTAs} per launch, taken round-robin from this
+// pool by the host (concurrent launches of one stream fork use different slots); a launch leaves
+// its slot zeroed.  sched_slot < 0: static striding (blockIdx.x + i * gridDim.x).
+constexpr int kSchedSlots = 256;
+constexpr int kTileRing = 16;                     // published work items a role may lag behind
+__device__ int g_tc2_sched[kSchedSlots * 2];
 constexpr int kTraceSteps = 256;
 __device__ long long* g_tc2_trace = nullptr;
 __device__ __forceinline__ void trace(long long* tr, int role, uint32_t step, int which) {
@@ -107,6 +113,7 @@ struct Layout {
   static constexpr bool kWide = PASSES == 3 && BN <= B200RL_TC2_WIDE_MAX_BN;
   static constexpr int kAccCols = kWide ? 2 * BN : BN;     // TMEM columns of one accumulator
   static constexpr int kBarBytes = 512;
+  static_assert(kStages + 4 <= kTileRing, "tile ring shorter than the deepest role lag");
   static constexpr int kBytes = kStages * kStage + 1024 /*alignment slack*/ + kBarBytes + BN * 4;
   static_assert(kStage % 1024 == 0, "stage planes must stay 1024 B aligned");
   static_assert(kStages >= 2, "at least two stages");
@@ -468,6 +475,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int act,
                     int beta, int splits, int64_t k_per_split, float* __restrict__ ws,
                     float out_scale, int64_t tiles_m, int64_t tiles_n, int epi_warps,
+                    int sched_slot,
                     const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB) {
   using L = Layout<BN, PASSES, AL::kExact>;
@@ -482,9 +490,11 @@ __global__ void __launch_bounds__(kThreads, 1)
   unsigned long long* empty = bars + 2 * S;       // MMAs of the stage retired -> loaders
   unsigned long long* acc_full = bars + 3 * S;    // [2] accumulator complete -> epilogue
   unsigned long long* acc_empty = acc_full + 2;   // [2] epilogue drained it -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  unsigned long long* tile_full = acc_empty + 2;  // [kTileRing] work item published
+  int* tile_slot = reinterpret_cast<int*>(tile_full + kTileRing);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tile_slot + kTileRing);
   float* scol = reinterpret_cast<float*>(smem + S * L::kStage + L::kBarBytes);   // [BN] column sums
-  static_assert((3 * 8 + 4) * 8 + 8 <= L::kBarBytes, "barrier block too small");
+  static_assert((3 * 8 + 4 + kTileRing) * 8 + kTileRing * 4 + 8 <= L::kBarBytes, "barrier block too small");
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   pdl_launch_dependents();
@@ -498,6 +508,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       mbar_init(smem_addr(&acc_full[i]), 1);
       mbar_init(smem_addr(&acc_empty[i]), (uint32_t)epi_warps);
     }
+    for (int i = 0; i < kTileRing; ++i) mbar_init(smem_addr(&tile_full[i]), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (tid < BN) scol[tid] = 0.f;
@@ -518,6 +529,21 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int64_t total = tiles_m * tiles_n * (int64_t)splits;
   long long* const tr = blockIdx.x == 0 ? g_tc2_trace : nullptr;
   const bool poll = (g_tc2_flags & 64) != 0;
+  // Work items: the first one of a CTA is blockIdx.x; with a scheduler slot the following ones come
+  // from a global counter (loader thread 0 fetches one item ahead and publishes each item in a
+  // shared-memory ring that every role reads), so a CTA that starts late -- its SM was busy with a
+  // collective or a kernel of the other stream -- simply takes fewer tiles instead of holding the
+  // whole launch back by its statically assigned share.
+  int* const sched = sched_slot >= 0 ? g_tc2_sched + 2 * sched_slot : nullptr;
+  auto next_tile = [&](uint32_t tq) -> int64_t {
+    if (sched == nullptr) {
+      const int64_t w = (int64_t)blockIdx.x + (int64_t)tq * gridDim.x;
+      return w < total ? w : -1;
+    }
+    const uint32_t slot = tq & (kTileRing - 1);
+    mbar_wait_hw(smem_addr(&tile_full[slot]), (tq / kTileRing) & 1u);
+    return *reinterpret_cast<volatile int*>(&tile_slot[slot]);
+  };
   constexpr bool kLoA = PASSES == 3 && !AL::kExact;
   constexpr bool kLoB = PASSES == 3;
   constexpr uint32_t kOffB = L::kNumA * L::kATile;
@@ -533,7 +559,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool use_tma = (g_tc2_flags & 4) == 0;   // bit 2: cp.async loaders for those as well (A/B)
     const bool no_load = (g_tc2_flags & 8) != 0;
     uint32_t it = 0;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    int64_t fetched = blockIdx.x;                   // scheduler (thread 0): the item to publish next
+    for (uint32_t tq = 0;; ++tq) {
+      if (sched != nullptr && tid == 0) {
+        const int v = fetched < total ? (int)fetched : -1;
+        const uint32_t slot = tq & (kTileRing - 1);
+        *reinterpret_cast<volatile int*>(&tile_slot[slot]) = v;
+        mbar_arrive(smem_addr(&tile_full[slot]));
+        if (v >= 0) {
+          fetched = (int64_t)gridDim.x + atomicAdd(sched, 1);   // used one tile later
+        } else if (atomicAdd(sched + 1, 1) == (int)gridDim.x - 1) {
+          atomicExch(sched, 0);                     // every CTA has drawn its last item: leave the
+          atomicExch(sched + 1, 0);                 // slot zeroed for its next launch
+        }
+      }
+      const int64_t w = next_tile(tq);
+      if (w < 0) break;
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
       if (AL::kTma2D && use_tma) ta.begin_tile(wk.m0);
       else la.begin_tile(a, wk.m0, M, tid);
@@ -563,7 +604,9 @@ __global__ void __launch_bounds__(kThreads, 1)
     const bool raw_hi = (g_tc2_flags & 1) == 0;
     const bool no_conv = (g_tc2_flags & 16) != 0;
     uint32_t it = 0;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x) {
+    for (uint32_t tq = 0;; ++tq) {
+      const int64_t w = next_tile(tq);
+      if (w < 0) break;
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
       const bool do_colsum = EPI == EPI_ATOMIC && !BL::kKContig && epi.colsum != nullptr && wk.first_m;
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -630,7 +673,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t fb_hi = (smem_base + kOffB) >> 4, fb_lo = (smem_base + kOffB + L::kBTile) >> 4;
       const bool no_mma = (g_tc2_flags & 32) != 0;
       uint32_t it = 0, tl = 0;
-      for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+      for (;; ++tl) {
+        const int64_t w = next_tile(tl);
+        if (w < 0) break;
         const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
         const uint32_t buf = tl & 1u;
         mbar_wait_tight(smem_addr(&acc_empty[buf]), ((tl >> 1) & 1u) ^ 1u, poll);
@@ -680,9 +725,22 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int chalf = (warp - kFirstEpiWarp) >> 2; // which part of the tile's columns it drains
     const int kColsPerWarp = BN / (epi_warps >> 2);
     uint32_t tl = 0;
-    for (int64_t w = blockIdx.x; w < total; w += gridDim.x, ++tl) {
+    for (;; ++tl) {
+      const int64_t w = next_tile(tl);
+      if (w < 0) break;
       const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
       const uint32_t buf = tl & 1u;
+      if (EPI == EPI_STORE && epi.mask.y != nullptr && splits == 1) {
+        // act' mask rows of this tile: start them towards L2 while the accumulator is still being
+        // produced (run 13: the mask loads sat behind every tcgen05.ld on the PPO dX GEMM)
+        const int64_t mm = wk.m0 + (warp & 3) * 32 + lane;
+        if (mm < M) {
+          const float* yrow = epi.mask.y + mm * epi.mask.ld + wk.n0;
+          const int c0 = ((warp - kFirstEpiWarp) >> 2) * (BN / (epi_warps >> 2));
+          for (int c = c0; c < c0 + BN / (epi_warps >> 2); c += 32)
+            if (wk.n0 + c < N) asm volatile("prefetch.global.L2 [%0];" ::"l"(yrow + c));
+        }
+      }
       mbar_wait_relaxed(smem_addr(&acc_full[buf]), (tl >> 1) & 1u, poll);
       if (warp == kFirstEpiWarp && lane == 0) trace(tr, 3, tl, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");

@@ -32,6 +32,14 @@ class SingleProcessStrategy(object):
     return 0, n
 
 
+def configure_nccl_env():
+  """Call before `init_process_group('nccl')`.  The gradient all-reduce runs beside the backward
+  pass, whose persistent GEMM kernels want every SM: cap NCCL at 8 CTAs (it holds 8 SMs instead of
+  16-32; measured on 2 B200s: 5305 -> 5403 steps/s with the dynamic tile scheduler).  A value
+  already in the environment wins."""
+  os.environ.setdefault('NCCL_MAX_CTAS', '8')
+
+
 class ProcessGroupStrategy(object):
   """Data parallelism over an initialised torch.distributed process group (nccl or gloo)."""
 
@@ -76,6 +84,7 @@ def get_strategy(tpu=None, use_gpu=True):
     backend = 'nccl' if (use_gpu and torch.cuda.is_available()) else 'gloo'
     if backend == 'nccl':
       torch.cuda.set_device(int(os.environ.get('LOCAL_RANK', '0')))
+      configure_nccl_env()
     dist.init_process_group(backend)
     return ProcessGroupStrategy()
   return SingleProcessStrategy()

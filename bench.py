@@ -302,6 +302,7 @@ def main():
   torch.cuda.set_device(local_rank)
   dev = torch.device('cuda', local_rank)
   if world > 1:
+    strategy_utils.configure_nccl_env()
     dist.init_process_group('nccl', device_id=dev)
   strategy = strategy_utils.get_strategy()
   W = max(args.warmup, 3)
@@ -487,7 +488,7 @@ def main():
   n_u = max(10, min(K, 50))
   ue0, ue1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
   # the update alone, replayed from its own graph so that the events bracket GPU time
-  train_only = common.function(lambda: agent.train(exp), warmup=1) if (use_graph and world == 1) else (
+  train_only = common.function(lambda: agent.train(exp), warmup=1) if use_graph else (
       lambda: agent.train(exp))
   for _ in range(3):
     train_only()
@@ -620,6 +621,10 @@ def main():
         scaling='weak', vs_baseline=None, dtype='f32 (3xTF32 tensor-core GEMMs, fp32 accumulate)', data='synthetic',
         config=dict(workload=WORKLOAD, global_batch=B * world, per_gpu_batch=B, num_actions=A,
                     parallelism=f'dp{world}' if world > 1 else 'single',
+                    multi_gpu=(None if world == 1 else
+                               f'gradient all-reduce in buckets of {agent._bucket_bytes} B on a side '
+                               f'stream beside the backward pass, dynamic GEMM tile scheduler, '
+                               f'NCCL_MAX_CTAS={os.environ.get("NCCL_MAX_CTAS")}'),
                     l2='inputs > L2: 29.6 GB ring, fresh random rows every step',
                     cuda_graph=bool(use_graph), collect_frames_per_e2e_step=B_ENV,
                     timing=f'median of {R} blocks of {K} graph replays, each block bracketed by '

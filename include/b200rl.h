@@ -357,6 +357,11 @@ int b200rl_tc_debug_variant(int v);
  * first-generation kernel (A/B comparisons in profiles/tc2_check.py).  bit 2: load plain 2-D
  * operands with cp.async like the im2col views instead of TMA tensor tiles. */
 int b200rl_set_tc2_flags(int flags);
+/* Work distribution of the persistent tcgen05 GEMM: 0 (default) static striding over the CTAs,
+ * 1 dynamic (global tile counter) -- set by the data-parallel Learner (train/learner.py:104-143 in
+ * the reference is where the strategy is attached) so that CTAs whose SM is held by the gradient
+ * all-reduce take fewer tiles; B200RL_TILE_SCHED=0/1 in the environment sets the initial value. */
+int b200rl_set_tile_scheduler(int dynamic);
 /* Profiling aid: CTA 0 of every tc2 GEMM stamps %globaltimer at the start/end of each pipeline
  * step of each role into dev_buf[4 roles][256 steps][2] (int64); NULL switches it off. */
 int b200rl_tc2_trace_buffer(long long* dev_buf);

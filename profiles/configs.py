@@ -394,6 +394,7 @@ if __name__ == '__main__':
   torch.cuda.set_device(local)
   dev = torch.device('cuda', local)
   if world > 1:
+    strategy_utils.configure_nccl_env()
     dist.init_process_group('nccl', device_id=dev)
   strategy = strategy_utils.get_strategy()
   pk = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(

@@ -139,6 +139,7 @@ def main():
   rank, world = int(os.environ['RANK']), int(os.environ['WORLD_SIZE'])
   torch.cuda.set_device(int(os.environ['LOCAL_RANK']))
   dev = torch.device('cuda', int(os.environ['LOCAL_RANK']))
+  strategy_utils.configure_nccl_env()
   dist.init_process_group('nccl', device_id=dev)
   strategy = strategy_utils.ProcessGroupStrategy()
   dqn_case(dev, strategy, rank, world)
