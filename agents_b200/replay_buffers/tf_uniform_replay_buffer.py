@@ -232,11 +232,16 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
 
   # ---- sample ---------------------------------------------------------------------------
   def _get_next(self, sample_batch_size=None, num_steps=None, time_stacked=True, ids=None,
-                batch_offsets=None):
+                batch_offsets=None, out=None):
     """Samples items uniformly (reference :211-310).
 
     Returns `(data, BufferInfo(ids, probabilities))`; data leaves are `[B, T, ...]`,
     `[B, ...]`, `[T, ...]` or `[...]` exactly as in the reference.
+
+    `out`: a `(data, BufferInfo)` pair returned by an earlier call with the same
+    `sample_batch_size` / `num_steps` (both given): the sample is written into those tensors --
+    the double buffer of a prefetching input pipeline (`dataset.prefetch` in the reference's
+    examples, agents/dqn/examples/v2/train_eval.py:226-232) without an allocation per step.
     """
     T = 1 if num_steps is None else int(num_steps)
     B = 1 if sample_batch_size is None else int(sample_batch_size)
@@ -255,10 +260,21 @@ class TFUniformReplayBuffer(replay_buffer.ReplayBuffer):
         ids = torch.as_tensor(ids, dtype=torch.int64, device=dev).reshape(B).contiguous()
         batch_offsets = torch.as_tensor(batch_offsets, dtype=torch.int64,
                                         device=dev).reshape(B).contiguous()
-      outs = [torch.empty((B, T) + s.shape, dtype=s.dtype, device=dev)
-              for s in self._flat_specs]
-      out_ids = torch.empty((B, T), dtype=torch.int64, device=dev)
-      probs = torch.empty((B,), dtype=torch.float32, device=dev)
+      if out is not None:
+        if sample_batch_size is None or num_steps is None or not time_stacked or not self._fused:
+          raise ValueError('out= needs sample_batch_size, num_steps and the fused sampler.')
+        outs = nest.flatten(out[0])
+        out_ids, probs = out[1].ids, out[1].probabilities
+        for t, s in zip(outs, self._flat_specs):
+          if tuple(t.shape) != (B, T) + tuple(s.shape) or t.dtype != s.dtype or not t.is_contiguous():
+            raise ValueError('out= does not match this sample shape.')
+        if tuple(out_ids.shape) != (B, T) or tuple(probs.shape) != (B,):
+          raise ValueError('out= does not match this sample shape.')
+      else:
+        outs = [torch.empty((B, T) + s.shape, dtype=s.dtype, device=dev)
+                for s in self._flat_specs]
+        out_ids = torch.empty((B, T), dtype=torch.int64, device=dev)
+        probs = torch.empty((B,), dtype=torch.float32, device=dev)
       if self._fused:
         out_ptrs = _lib.ptr_array(outs)
         _lib.call('b200rl_rb_sample', ctypes.byref(self._ring), B, T, _lib.ptr(ids),

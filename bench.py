@@ -273,6 +273,9 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip configs 1/3/4/5 and dp_parity')
+  ap.add_argument('--no-prefetch', action='store_true',
+                  help='sample and train back to back on one stream (default: the sample of step '
+                       'i+1 runs on a side stream beside train(i), like dataset.prefetch(1))')
   ap.add_argument('--ncu-step', action='store_true',
                   help='after warm-up run ONE un-captured step between cudaProfilerStart/Stop and '
                        'exit (target of `ncu --profile-from-start off`; prints no bench value)')
@@ -382,9 +385,38 @@ def main():
     if not parity['ok']:
       sys.stderr.write(f'PARITY FAILED at the bench config: {parity}\n')
 
-  def step():
+  # Input pipeline.  The reference's examples train from `replay_buffer.as_dataset(...).prefetch(n)`
+  # (agents/dqn/examples/v2/train_eval.py:226-232): the next batch is produced while the current
+  # one trains.  Here: two sample buffers; step i trains on buffer i & 1 while the sampler fills
+  # the other one on a side stream (same Philox draw order as back-to-back calls).  Every step
+  # still contains one sample and one train.
+  prefetch = not args.no_prefetch
+  side_stream = torch.cuda.Stream(device=dev)
+  sample_bufs = [rb.get_next(sample_batch_size=B, num_steps=T) for _ in range(2)]
+  step_no = [0]
+
+  def pipelined(slot):
+    def body():
+      main = torch.cuda.current_stream()
+      side_stream.wait_stream(main)
+      with torch.cuda.stream(side_stream):
+        rb.get_next(sample_batch_size=B, num_steps=T, out=sample_bufs[slot ^ 1])
+      loss_ = agent.train(sample_bufs[slot][0]).loss
+      main.wait_stream(side_stream)
+      return loss_
+    return body
+
+  def serial_step():
     exp, _ = rb.get_next(sample_batch_size=B, num_steps=T)
     return agent.train(exp).loss
+
+  bodies = [pipelined(0), pipelined(1)]
+
+  def step():
+    if not prefetch:
+      return serial_step()
+    step_no[0] += 1
+    return bodies[(step_no[0] - 1) & 1]()
 
   def sync_all():
     if world > 1:
@@ -400,11 +432,22 @@ def main():
   launches_per_step = _lib.launch_count() - c0
 
   use_graph = not args.no_graph
-  fn = common.function(step, warmup=1) if use_graph else step
+  if use_graph and prefetch:
+    graphs = [common.function(b, warmup=1) for b in bodies]
+
+    def fn():
+      step_no[0] += 1
+      return graphs[(step_no[0] - 1) & 1]()
+  else:
+    fn = common.function(step, warmup=1) if use_graph else step
   fn()                                   # eager warm-up call (sizes workspaces)
+  if use_graph and prefetch:
+    fn()                                 # ... of the second buffer's graph as well
   ok = 1
   try:
     fn()                                 # capture + first replay
+    if use_graph and prefetch:
+      fn()
   except Exception as e:  # a step that cannot be captured on this stack -> eager
     if not use_graph:
       raise
@@ -562,9 +605,20 @@ def main():
     d = staged[slot]
 
     def f():
-      rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
-      exp_, _ = rb.get_next(sample_batch_size=B, num_steps=T)
-      return agent.train(exp_).loss
+      if not prefetch:
+        rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
+        exp_, _ = rb.get_next(sample_batch_size=B, num_steps=T)
+        return agent.train(exp_).loss
+      # collect-side work of this step (store the uploaded frames, draw the next batch) beside
+      # the update on the batch drawn one step earlier
+      main = torch.cuda.current_stream()
+      side_stream.wait_stream(main)
+      with torch.cuda.stream(side_stream):
+        rb.add_batch(trajectory.Trajectory(d[0], d[1], d[2], (), d[3], d[4], d[5]))
+        rb.get_next(sample_batch_size=B, num_steps=T, out=sample_bufs[slot ^ 1])
+      loss_ = agent.train(sample_bufs[slot][0]).loss
+      main.wait_stream(side_stream)
+      return loss_
     return common.function(f, warmup=1)
 
   e2e_fns = [_fused(0), _fused(1)] if (use_graph and world == 1) else None
@@ -594,8 +648,11 @@ def main():
 
   # ---- the other BASELINE configs (ring freed first: config 5 needs the HBM) --------------------
   del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only, e2e_fns
+  del sample_bufs, bodies
   if use_graph:
     del fn
+    if prefetch:
+      del graphs
   torch.cuda.empty_cache()
   if not args.no_extra:
     from profiles import configs
@@ -627,6 +684,8 @@ def main():
                                f'NCCL_MAX_CTAS={os.environ.get("NCCL_MAX_CTAS")}'),
                     l2='inputs > L2: 29.6 GB ring, fresh random rows every step',
                     cuda_graph=bool(use_graph), collect_frames_per_e2e_step=B_ENV,
+                    input_pipeline=('prefetch(1): sample of step i+1 on a side stream beside train(i), two '
+                                    'sample buffers' if prefetch else 'sample then train on one stream'),
                     timing=f'median of {R} blocks of {K} graph replays, each block bracketed by '
                            'barrier + synchronize, CUDA events, max over ranks',
                     e2e_pipeline='pinned host frames -> double-buffered H2D on a copy stream -> '
