@@ -104,6 +104,10 @@ SIGNATURES = {
     'b200rl_set_tile_scheduler': [c_int],
     'b200rl_tc2_trace_buffer': [_P],
     'b200rl_dense_fwd': [_P, c_i64, _P, _P, _P, c_i64, c_i64, c_i64, c_int, _P, c_i64, _P],
+    'b200rl_dense_fwd_pair': [_P, _P, c_i64, _P, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_int, _P,
+                              c_i64, _P],
+    'b200rl_conv2d_fwd_pair': [_P, _P, c_int, c_f32, _P, _P, _P, _P, _P, _P,
+                               ctypes.POINTER(ConvGeom), c_int, _P, c_i64, _P],
     'b200rl_dense_bwd': [_P, c_i64, _P, _P, _P, _P, _P, c_i64, c_i64, c_i64, c_int, c_int, _P, c_i64,
                          _P],
     'b200rl_act_bwd': [_P, _P, _P, c_i64, c_int, _P],

@@ -111,6 +111,11 @@ class DqnAgent(tf_agent.TFAgent):
     # 0 = never, 1 = inside common.function graphs (default), 2 = always
     self._overlap_target = int(os.environ.get('B200RL_DQN_OVERLAP', '1'))
     self._side_stream = torch.cuda.Stream(device=device) if self._overlap_target else None
+    # B200RL_DQN_PAIR_FWD=1: online + target forward as paired launches (Network.forward_pair).
+    # Off by default: measured SLOWER than the two-stream fork below (run 19: 2806 vs 2890
+    # steps/s, 25 vs 29 launches per step) -- with the target pass on its own stream the fill and
+    # drain of one network's kernels hide behind the other's, which the single paired launch loses.
+    self._pair_forward = int(os.environ.get('B200RL_DQN_PAIR_FWD', '0'))
     self._clip_offsets = None
     self.replicas = 1           # set by train.Learner for data-parallel runs
     self._grad_sync = None      # callable(flat_grads) installed by train.Learner
@@ -179,6 +184,16 @@ class DqnAgent(tf_agent.TFAgent):
     # stream (also inside a captured graph) and join before the TD kernel.
     main = torch.cuda.current_stream()
     side = None
+    # Plain DQN: the online forward on obs[:, 0] and the target forward on obs[:, T-1] are two
+    # passes through identical layer stacks -> every layer pair is one launch.
+    if (self._pair_forward and not self._DOUBLE_Q and keep_tape and
+        self._q_network.pairs_with(self._target_q_network) and
+        hasattr(self._q_network, 'forward_pair')):
+      (q, tape), next_t = self._q_network.forward_pair(self._target_q_network, obs0, obsn)
+      if not isinstance(q, tuple) and not isinstance(next_t, tuple):
+        if self._SELECT_UNMASKED:
+          next_mask = None
+        return self._td(exp, B, T, q, next_t, next_t, next_mask, weights, tape)
     if self._overlap_target == 2 or (self._overlap_target and
                                      torch.cuda.is_current_stream_capturing()):
       # eager launches are host-bound, the fork only pays inside a captured graph
@@ -205,6 +220,10 @@ class DqnAgent(tf_agent.TFAgent):
       main.wait_stream(side)
     elif self._overlap_target and not torch.cuda.is_current_stream_capturing():
       workspace.mirror(q.device, 1)   # size the side-stream scratch for a later capture
+    return self._td(exp, B, T, q, next_t, next_sel, next_mask, weights, tape)
+
+  def _td(self, exp, B, T, q, next_t, next_sel, next_mask, weights, tape):
+    """TD targets, element-wise loss and dLoss/dq from the three Q tables (one kernel)."""
     dev = q.device
     # [:, 0] columns of the [B, T] tensors are read in place (no gather/cast launches)
     actions, a_stride = self._column0(exp.action)

@@ -1069,8 +1069,28 @@ static int tmap_for(const BCol& v, int64_t rows, int64_t K, int box_rows, CUtens
   return tmap_2d(v.p, rows, K, v.ld, box_rows, out);
 }
 
+// operand base pointers (pair launches pass the second problem as byte offsets from the first)
+static const void* view_base(const ARow& v) { return v.p; }
+static const void* view_base(const ACol& v) { return v.p; }
+static const void* view_base(const BRow& v) { return v.p; }
+static const void* view_base(const BCol& v) { return v.p; }
+template <class T> static const void* view_base(const AConv<T>& v) { return v.v.x; }
+template <class T> static const void* view_base(const AConvT<T>& v) { return v.v.x; }
+static const void* view_base(const AConvU8Raw& v) { return v.v.x; }
+static const void* view_base(const AConvTU8Raw& v) { return v.v.x; }
+
+// second problem of a pair launch (same shapes, see tc2::PairArgs)
+template <class AL, class BL>
+struct Tc2Pair {
+  AL a;
+  BL b;
+  float* C;
+  const float* bias;
+};
+
 template <int BN, int PASSES, int EPI, class AL, class BL>
-static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
+static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi,
+                          const Tc2Pair<AL, BL>* pair = nullptr) {
   using L = tc2::Layout<BN, PASSES, AL::kExact>;
   auto kernel = tc2::tc2_gemm_kernel<BN, PASSES, EPI, AL, BL>;
   static bool configured = false;
@@ -1083,14 +1103,15 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
     }
     configured = true;
   }
-  const int64_t tm = (g.M + tc::kBM - 1) / tc::kBM, tn = (g.N + BN - 1) / BN;
+  const int64_t tm1 = (g.M + tc::kBM - 1) / tc::kBM, tn = (g.N + BN - 1) / BN;
+  const int64_t tm = pair ? 2 * tm1 : tm1;
   const int64_t tiles = tm * tn;
   int splits = 1;
   const int64_t target = kNumSMs;                  // one persistent CTA per SM
   if (tiles < target && g.K >= 8 * tc::kBK && (g.ws != nullptr || EPI != tc::EPI_STORE)) {
     int64_t want = target / tiles;
     int64_t max_by_k = g.K / (4 * tc::kBK);
-    int64_t max_by_ws = EPI != tc::EPI_STORE ? 65535 : g.ws_bytes / (int64_t)(g.M * g.N * sizeof(float));
+    int64_t max_by_ws = EPI != tc::EPI_STORE ? 65535 : g.ws_bytes / (int64_t)((pair ? 2 : 1) * g.M * g.N * sizeof(float));
     int64_t s = want < max_by_k ? want : max_by_k;
     if (s > max_by_ws) s = max_by_ws;
     if (s >= 2) splits = (int)s;
@@ -1102,11 +1123,24 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   const int64_t total = tiles * splits;
   B200RL_CHECK_ARG(total < (1ll << 31), "tc2_gemm: too many work items");
   const unsigned grid = (unsigned)(total < kNumSMs ? total : kNumSMs);
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA2, tmB2;
   int rc = tmap_for(a, g.M, g.K, tc::kBM, &tmA);
   if (rc) return rc;
   rc = tmap_for(b, g.N, g.K, BN, &tmB);
   if (rc) return rc;
+  tmA2 = tmA;
+  tmB2 = tmB;
+  tc2::PairArgs pa{tm1, 0, 0, 0, 0};
+  if (pair) {
+    rc = tmap_for(pair->a, g.M, g.K, tc::kBM, &tmA2);
+    if (rc) return rc;
+    rc = tmap_for(pair->b, g.N, g.K, BN, &tmB2);
+    if (rc) return rc;
+    pa.a_delta = (const char*)view_base(pair->a) - (const char*)view_base(a);
+    pa.b_delta = (const char*)view_base(pair->b) - (const char*)view_base(b);
+    pa.c_delta = pair->C - g.C;
+    pa.bias_delta = (g.bias && pair->bias) ? pair->bias - g.bias : 0;
+  }
   // epilogue-bound shapes (col2im scatter-add, short K loops) get all eight epilogue warps
   static const int epi_env = [] { const char* e = getenv("B200RL_TC2_EPI_WARPS"); return e ? atoi(e) : 0; }();
   const int epi_warps = (epi_env == 4 || epi_env == 8) ? epi_env
@@ -1115,22 +1149,27 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   static int sched_seq = 0;
   int sched_slot = -1;
   if (total > grid && tile_scheduler_dynamic()) sched_slot = (sched_seq++) & (tc2::kSchedSlots - 1);
-  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, epi_warps, sched_slot, tmA, tmB);
+  B200RL_LAUNCH(kernel, grid, tc2::kThreads, L::kBytes, g.st, a, b, epi, g.C, g.bias, g.M, g.N, g.K, g.act, g.beta, splits, kps, (float*)g.ws, g.out_scale, tm, tn, epi_warps, sched_slot, pa, tmA, tmB, tmA2, tmB2);
   B200RL_CHECK_LAUNCH("tc2_gemm");
   if (splits > 1 && EPI == tc::EPI_STORE) {
     const int64_t MN = g.M * g.N;
     B200RL_LAUNCH(splitk_reduce_kernel, (unsigned)((MN + 255) / 256), 256, 0, g.st, (const float*)g.ws, g.C, g.bias, MN, g.N, splits, g.act, g.beta, g.mask);
     B200RL_CHECK_LAUNCH("splitk_reduce");
+    if (pair) {
+      B200RL_LAUNCH(splitk_reduce_kernel, (unsigned)((MN + 255) / 256), 256, 0, g.st, (const float*)g.ws + (int64_t)splits * MN, pair->C, pair->bias, MN, g.N, splits, g.act, g.beta, g.mask);
+      B200RL_CHECK_LAUNCH("splitk_reduce");
+    }
   }
   return B200RL_OK;
 }
 
 // BN by N like the first-generation dispatch
 template <int PASSES, int EPI, class AL, class BL>
-static int launch_tc2(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi) {
-  if (g.N <= 32) return launch_tc2_cfg<32, PASSES, EPI>(a, b, g, epi);
-  if (g.N <= 64) return launch_tc2_cfg<64, PASSES, EPI>(a, b, g, epi);
-  return launch_tc2_cfg<128, PASSES, EPI>(a, b, g, epi);
+static int launch_tc2(const AL& a, const BL& b, const GemmArgs& g, const tc::EpiArgs& epi,
+                      const Tc2Pair<AL, BL>* pair = nullptr) {
+  if (g.N <= 32) return launch_tc2_cfg<32, PASSES, EPI>(a, b, g, epi, pair);
+  if (g.N <= 64) return launch_tc2_cfg<64, PASSES, EPI>(a, b, g, epi, pair);
+  return launch_tc2_cfg<128, PASSES, EPI>(a, b, g, epi, pair);
 }
 template <class V> struct Tc2Capable { static constexpr bool value = true; };
 template <> struct Tc2Capable<AConv<uint8_t>> { static constexpr bool value = false; };
@@ -1305,6 +1344,32 @@ static int make_geom(const b200rl_conv_t* c, ConvGeom& g) {
 
 using namespace b200rl;
 
+// Forward pass of TWO layers of identical shape in one launch (DQN: the online network on
+// obs[:, 0] and the target network on obs[:, T-1]).  Falls back to two launches whenever the
+// persistent tensor-core kernel does not take the shape.
+static int pair_fwd_enabled() {
+  static const int v = [] { const char* e = getenv("B200RL_PAIR_FWD"); return e ? atoi(e) : 1; }();
+  return v;
+}
+template <class AL, class BL>
+static int launch_fwd_pair(const AL& a1, const BL& b1, const GemmArgs& g1, const AL& a2,
+                           const BL& b2, const GemmArgs& g2) {
+  const int mode = gemm_mode();
+  if constexpr (Tc2Capable<AL>::value) {
+    if (pair_fwd_enabled() && mode != 0 && g1.N >= 16 && g1.M >= 32 && g1.K >= 8 &&
+        use_tc2(a1, b1, g1) && use_tc2(a2, b2, g2) && (g1.bias == nullptr) == (g2.bias == nullptr)) {
+      tc::EpiArgs none{};
+      Tc2Pair<AL, BL> p{a2, b2, g2.C, g2.bias};
+      if (mode == 2) return launch_tc2<1, tc::EPI_STORE>(a1, b1, g1, none, &p);
+      return launch_tc2<3, tc::EPI_STORE>(a1, b1, g1, none, &p);
+    }
+  }
+  int rc = launch_gemm(a1, b1, g1);
+  if (rc) return rc;
+  return launch_gemm(a2, b2, g2);
+}
+
+
 extern "C" {
 
 int b200rl_tc_debug_buffer(long long* dev_buf) {
@@ -1407,6 +1472,22 @@ int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* b
   return launch_gemm(ARow{X, ldx ? ldx : K}, BRow{W, N}, g);
 }
 
+int b200rl_dense_fwd_pair(const float* X1, const float* X2, int64_t ldx, const float* W1,
+                          const float* W2, const float* bias1, const float* bias2, float* Y1,
+                          float* Y2, int64_t M, int64_t K, int64_t N, int act, void* workspace,
+                          int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X1 && X2 && W1 && W2 && Y1 && Y2, "dense_fwd_pair: NULL argument");
+  B200RL_CHECK_ARG(ldx == 0 || ldx >= K, "dense_fwd_pair: ldx < K");
+  if (skinny_ok(M, K, N) || (thin_ok(X1, ldx, W1, M, K, N) && thin_ok(X2, ldx, W2, M, K, N))) {
+    int rc = b200rl_dense_fwd(X1, ldx, W1, bias1, Y1, M, K, N, act, workspace, ws_bytes, stream);
+    if (rc) return rc;
+    return b200rl_dense_fwd(X2, ldx, W2, bias2, Y2, M, K, N, act, workspace, ws_bytes, stream);
+  }
+  GemmArgs g1{Y1, bias1, M, N, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  GemmArgs g2{Y2, bias2, M, N, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  return launch_fwd_pair(ARow{X1, ldx ? ldx : K}, BRow{W1, N}, g1, ARow{X2, ldx ? ldx : K}, BRow{W2, N}, g2);
+}
+
 int b200rl_dense_bwd(const float* X, int64_t ldx, const float* W, const float* dY, float* dX,
                      float* dW, float* db, int64_t M, int64_t K, int64_t N, int accumulate,
                      int x_act, void* workspace, int64_t ws_bytes, void* stream) {
@@ -1486,6 +1567,42 @@ int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt
   }
   AConv<float> a{ConvView<float>{(const float*)X, cg, 1.f}};
   return launch_gemm(a, BRow{Wt, c->F}, g);
+}
+
+int b200rl_conv2d_fwd_pair(const void* X1, const void* X2, int x_is_u8, float x_scale,
+                           const float* Wt1, const float* Wt2, const float* bias1,
+                           const float* bias2, float* Y1, float* Y2, const b200rl_conv_t* c,
+                           int act, void* workspace, int64_t ws_bytes, void* stream) {
+  B200RL_CHECK_ARG(X1 && X2 && Wt1 && Wt2 && Y1 && Y2, "conv2d_fwd_pair: NULL argument");
+  ConvGeom cg;
+  int rc = make_geom(c, cg);
+  if (rc) return rc;
+  const int64_t M = (int64_t)c->N * cg.OH * cg.OW, K = (int64_t)c->KH * c->KW * c->C;
+  GemmArgs g1{Y1, bias1, M, c->F, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  GemmArgs g2{Y2, bias2, M, c->F, K, act, 0, workspace, ws_bytes, (cudaStream_t)stream};
+  if (x_is_u8) {
+    if (gemm_mode() == 1 && c->F >= 16 && M >= 32 && K >= 8) {   // raw pixels, 2-pass 3xTF32
+      g1.out_scale = g2.out_scale = 1.f / x_scale;
+      AConvU8Raw a1{ConvView<uint8_t>{(const uint8_t*)X1, cg, x_scale}};
+      AConvU8Raw a2{ConvView<uint8_t>{(const uint8_t*)X2, cg, x_scale}};
+      const BRow b1{Wt1, c->F}, b2{Wt2, c->F};
+      if (pair_fwd_enabled() && use_tc2(a1, b1, g1) && use_tc2(a2, b2, g2) &&
+          (bias1 == nullptr) == (bias2 == nullptr)) {
+        tc::EpiArgs none{};
+        Tc2Pair<AConvU8Raw, BRow> p{a2, b2, Y2, bias2};
+        return launch_tc2<3, tc::EPI_STORE>(a1, b1, g1, none, &p);
+      }
+      rc = launch_tc<3>(a1, b1, g1);
+      if (rc) return rc;
+      return launch_tc<3>(a2, b2, g2);
+    }
+    rc = b200rl_conv2d_fwd(X1, x_is_u8, x_scale, Wt1, bias1, Y1, c, act, workspace, ws_bytes, stream);
+    if (rc) return rc;
+    return b200rl_conv2d_fwd(X2, x_is_u8, x_scale, Wt2, bias2, Y2, c, act, workspace, ws_bytes, stream);
+  }
+  AConv<float> a1{ConvView<float>{(const float*)X1, cg, 1.f}};
+  AConv<float> a2{ConvView<float>{(const float*)X2, cg, 1.f}};
+  return launch_fwd_pair(a1, BRow{Wt1, c->F}, g1, a2, BRow{Wt2, c->F}, g2);
 }
 
 int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt,

@@ -198,15 +198,28 @@ __device__ __forceinline__ void mbar_wait_tight(uint32_t bar, uint32_t parity, b
 struct Work {
   int64_t m0, n0, kb, ke;
   int split, nkb;
-  bool first_m;
+  bool first_m, second;
+};
+// Two problems of identical shape in one launch (DQN: the online network on obs[:, 0] and the
+// target network on obs[:, T-1] -- same layers, different inputs and weights): m-tiles
+// [tiles_m1, 2 tiles_m1) belong to the second problem, whose operands / outputs sit at fixed
+// offsets from the first one's.  One launch instead of two saves the exposed fill + drain of a
+// kernel boundary (~4-5 us on these layers) and halves the tile-count rounding loss.
+struct PairArgs {
+  int64_t tiles_m1;          // m-tiles of ONE problem (== tiles_m when the launch is not a pair)
+  int64_t a_delta, b_delta;  // BYTES from the first problem's operand base to the second's
+  int64_t c_delta, bias_delta;  // ELEMENTS between the outputs / biases
 };
 __device__ __forceinline__ Work decode_work(int64_t w, int64_t tiles_m, int64_t tiles_n, int BN,
-                                            int64_t K, int64_t k_per_split) {
+                                            int64_t K, int64_t k_per_split, int64_t tiles_m1) {
   Work o;
   // 32-bit arithmetic (the host checks tiles * splits < 2^31): a 64-bit division is a call
   const uint32_t tiles_mn = (uint32_t)(tiles_m * tiles_n), wi = (uint32_t)w, tn_ = (uint32_t)tiles_n;
   const uint32_t split = wi / tiles_mn, rem = wi - split * tiles_mn;
-  const uint32_t tm = rem / tn_, tn = rem - tm * tn_;            // n fastest: neighbours share A rows
+  uint32_t tm = rem / tn_;
+  const uint32_t tn = rem - tm * tn_;                           // n fastest: neighbours share A rows
+  o.second = tm >= (uint32_t)tiles_m1;
+  if (o.second) tm -= (uint32_t)tiles_m1;
   o.split = (int)split;
   o.m0 = (int64_t)tm * kBM;
   o.n0 = (int64_t)tn * BN;
@@ -228,7 +241,8 @@ struct LoadKContigF32 {
   const char* rowp[NR];                            // element (row, 0); rows past the edge: row 0
   uint32_t ok, dst0;
   int j;
-  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t,
+                                             int64_t delta) {
     j = t & 7;
     const int r0 = t >> 3;
     dst0 = tc::sw128((uint32_t)r0, (uint32_t)j);
@@ -237,7 +251,7 @@ struct LoadKContigF32 {
     for (int i = 0; i < NR; ++i) {
       const int64_t r = row0 + r0 + RPP * i;
       const bool in = r < row_limit;
-      rowp[i] = reinterpret_cast<const char*>(v.addr(in ? v.row_off(r) : 0));
+      rowp[i] = reinterpret_cast<const char*>(v.addr(in ? v.row_off(r) : 0)) + delta;
       ok |= (in ? 1u : 0u) << i;
     }
   }
@@ -265,12 +279,13 @@ struct LoadMnF32 {                                 // LROWS: rows of the shared-
   uint32_t dst[NC];
   bool ok;
   int kk0;
-  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t,
+                                             int64_t delta) {
     const int cm = t % CPR;
     kk0 = t / CPR;
     const int64_t r = row0 + 4 * cm;
     ok = r < row_limit;                            // rows % 4 == 0 (host check)
-    rowp = reinterpret_cast<const char*>(v.addr(ok ? v.row_off(r) : 0));
+    rowp = reinterpret_cast<const char*>(v.addr(ok ? v.row_off(r) : 0)) + delta;
 #pragma unroll
     for (int i = 0; i < NC; ++i) dst[i] = tc::mn128<LROWS>((uint32_t)cm, (uint32_t)(kk0 + KSTEP * i));
   }
@@ -306,7 +321,10 @@ struct LoadKContigU8 {
   bool ok;
   uint32_t dst;
   int h;
-  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+  int64_t delta;
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t,
+                                             int64_t delta_) {
+    delta = delta_;
     const int row = t >> 1;
     h = t & 1;
     const int64_t r = row0 + row;
@@ -318,7 +336,8 @@ struct LoadKContigU8 {
   __device__ __forceinline__ void issue(const V& v, uint32_t raw, int64_t k0, int64_t ke) {
     const int64_t k = k0 + 16 * h;
     const bool in = ok && k < ke;                  // K % 16 == 0 (host check)
-    cp_async16(raw + dst, v.addr(in ? roff + v.k_off(k) : 0), in ? 16u : 0u);
+    cp_async16(raw + dst, reinterpret_cast<const char*>(v.addr(in ? roff + v.k_off(k) : 0)) + delta,
+               in ? 16u : 0u);
   }
 };
 
@@ -330,7 +349,10 @@ struct LoadMnU8 {
   int64_t roff;
   bool ok;
   int c, kk0;
-  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t) {
+  int64_t delta;
+  __device__ __forceinline__ void begin_tile(const V& v, int64_t row0, int64_t row_limit, int t,
+                                             int64_t delta_) {
+    delta = delta_;
     c = t & 7;
     kk0 = t >> 3;
     const int64_t r = row0 + 16 * c;
@@ -345,7 +367,7 @@ struct LoadMnU8 {
     const bool in = ok && (k0 + kk < ke);
     // slot c ^ 2(kk & 3): see convert_u8_mn
     cp_async16(raw + (uint32_t)kk * 128u + (((uint32_t)c ^ (((uint32_t)kk & 3u) << 1)) << 4),
-               v.addr(in ? roff + koff : 0), in ? 16u : 0u);
+               reinterpret_cast<const char*>(v.addr(in ? roff + koff : 0)) + delta, in ? 16u : 0u);
   }
 };
 
@@ -475,9 +497,11 @@ __global__ void __launch_bounds__(kThreads, 1)
                     const float* __restrict__ bias, int64_t M, int64_t N, int64_t K, int act,
                     int beta, int splits, int64_t k_per_split, float* __restrict__ ws,
                     float out_scale, int64_t tiles_m, int64_t tiles_n, int epi_warps,
-                    int sched_slot,
+                    int sched_slot, const PairArgs pair,
                     const __grid_constant__ CUtensorMap tmA,
-                    const __grid_constant__ CUtensorMap tmB) {
+                    const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmA2,
+                    const __grid_constant__ CUtensorMap tmB2) {
   using L = Layout<BN, PASSES, AL::kExact>;
   constexpr int S = L::kStages;
   extern __shared__ unsigned char smem_raw[];
@@ -558,7 +582,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     LoadTma2D<BN> tb;
     const bool use_tma = (g_tc2_flags & 4) == 0;   // bit 2: cp.async loaders for those as well (A/B)
     const bool no_load = (g_tc2_flags & 8) != 0;
-    uint32_t it = 0;
+    uint32_t it = 0, ring_s = 0, ring_ph = 0;      // stage / phase of K block `it` without a division
     int64_t fetched = blockIdx.x;                   // scheduler (thread 0): the item to publish next
     for (uint32_t tq = 0;; ++tq) {
       if (sched != nullptr && tid == 0) {
@@ -575,23 +599,24 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
       const int64_t w = next_tile(tq);
       if (w < 0) break;
-      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split, pair.tiles_m1);
       if (AL::kTma2D && use_tma) ta.begin_tile(wk.m0);
-      else la.begin_tile(a, wk.m0, M, tid);
+      else la.begin_tile(a, wk.m0, M, tid, wk.second ? pair.a_delta : 0);
       if (BL::kTma2D && use_tma) tb.begin_tile(wk.n0);
-      else lb.begin_tile(b, wk.n0, N, tid);
+      else lb.begin_tile(b, wk.n0, N, tid, wk.second ? pair.b_delta : 0);
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
-        const uint32_t s = it % S, ph = (it / S) & 1u;
+        const uint32_t s = ring_s, ph = ring_ph;
+        if (++ring_s == S) { ring_s = 0; ring_ph ^= 1u; }
         mbar_wait_relaxed(smem_addr(&empty[s]), ph ^ 1u, poll);
         if (tid == 0) trace(tr, 0, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
         const int64_t k0 = wk.kb + (int64_t)kbi * kBK;
         const uint32_t bar = smem_addr(&raw_full[s]);
         if (!no_load) {
-          if (AL::kTma2D && use_tma) ta.issue(&tmA, st, k0, bar);
+          if (AL::kTma2D && use_tma) ta.issue(wk.second ? &tmA2 : &tmA, st, k0, bar);
           else la.issue(a, AL::kExact ? st + kOffRaw : st, k0, wk.ke);
-          if (BL::kTma2D && use_tma) tb.issue(&tmB, st + kOffB, k0, bar);
+          if (BL::kTma2D && use_tma) tb.issue(wk.second ? &tmB2 : &tmB, st + kOffB, k0, bar);
           else lb.issue(b, st + kOffB, k0, wk.ke);
         }
         cp_async_arrive(smem_addr(&raw_full[s]));
@@ -603,16 +628,17 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int t = tid - kLoaderThreads;
     const bool raw_hi = (g_tc2_flags & 1) == 0;
     const bool no_conv = (g_tc2_flags & 16) != 0;
-    uint32_t it = 0;
+    uint32_t it = 0, ring_s = 0, ring_ph = 0;
     for (uint32_t tq = 0;; ++tq) {
       const int64_t w = next_tile(tq);
       if (w < 0) break;
-      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split, pair.tiles_m1);
       const bool do_colsum = EPI == EPI_ATOMIC && !BL::kKContig && epi.colsum != nullptr && wk.first_m;
       float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 1
       for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
-        const uint32_t s = it % S, ph = (it / S) & 1u;
+        const uint32_t s = ring_s, ph = ring_ph;
+        if (++ring_s == S) { ring_s = 0; ring_ph ^= 1u; }
         mbar_wait_tight(smem_addr(&raw_full[s]), ph, poll);
         if (t == 0) trace(tr, 1, it, 0);
         const uint32_t st = smem_base + s * L::kStage;
@@ -672,18 +698,19 @@ __global__ void __launch_bounds__(kThreads, 1)
       const uint32_t fa_hi = smem_base >> 4, fa_lo = (smem_base + L::kATile) >> 4;
       const uint32_t fb_hi = (smem_base + kOffB) >> 4, fb_lo = (smem_base + kOffB + L::kBTile) >> 4;
       const bool no_mma = (g_tc2_flags & 32) != 0;
-      uint32_t it = 0, tl = 0;
+      uint32_t it = 0, tl = 0, ring_s = 0, ring_ph = 0;
       for (;; ++tl) {
         const int64_t w = next_tile(tl);
         if (w < 0) break;
-        const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+        const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split, pair.tiles_m1);
         const uint32_t buf = tl & 1u;
         mbar_wait_tight(smem_addr(&acc_empty[buf]), ((tl >> 1) & 1u) ^ 1u, poll);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t tmem_d = tmem_base + buf * L::kAccCols;
 #pragma unroll 1
         for (int kbi = 0; kbi < wk.nkb; ++kbi, ++it) {
-          const uint32_t s = it % S, ph = (it / S) & 1u;
+          const uint32_t s = ring_s, ph = ring_ph;
+        if (++ring_s == S) { ring_s = 0; ring_ph ^= 1u; }
           mbar_wait_tight(smem_addr(&conv_full[s]), ph, poll);
           trace(tr, 2, it, 0);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic stores -> async proxy
@@ -728,7 +755,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     for (;; ++tl) {
       const int64_t w = next_tile(tl);
       if (w < 0) break;
-      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split);
+      const Work wk = decode_work(w, tiles_m, tiles_n, BN, K, k_per_split, pair.tiles_m1);
       const uint32_t buf = tl & 1u;
       if (EPI == EPI_STORE && epi.mask.y != nullptr && splits == 1) {
         // act' mask rows of this tile: start them towards L2 while the accumulator is still being
@@ -745,7 +772,10 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (warp == kFirstEpiWarp && lane == 0) trace(tr, 3, tl, 0);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int64_t m = wk.m0 + q * 32 + lane;
-      float* out = (splits > 1 && EPI == EPI_STORE) ? ws + (int64_t)wk.split * M * N : C;
+      float* const Cx = C + (wk.second ? pair.c_delta : 0);
+      const float* const biasx = bias ? bias + (wk.second ? pair.bias_delta : 0) : nullptr;
+      float* out = (splits > 1 && EPI == EPI_STORE)
+                       ? ws + ((int64_t)(wk.second ? splits : 0) + wk.split) * M * N : Cx;
       const bool vec_out = (N & 3) == 0 && ((uintptr_t)out & 15) == 0;
       const bool final_pass = splits == 1;
       const bool vec_mask = (N & 3) == 0 && (epi.mask.ld & 3) == 0 && ((uintptr_t)epi.mask.y & 15) == 0;
@@ -804,7 +834,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                          : "memory");
           }
         } else if (EPI == EPI_ATOMIC) {
-          float* dst = C + m * N + nb;
+          float* dst = Cx + m * N + nb;
           if ((N & 3) == 0) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -827,9 +857,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * out_scale;
           if (final_pass) {
             const bool full = nb + 15 < N;
-            if (bias) {
+            if (biasx) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j) v[j] += (full || nb + j < N) ? __ldg(bias + nb + j) : 0.f;
+              for (int j = 0; j < 16; ++j) v[j] += (full || nb + j < N) ? __ldg(biasx + nb + j) : 0.f;
             }
             if (act == B200RL_ACT_RELU) {
 #pragma unroll

@@ -205,6 +205,35 @@ class Network(object):
     out, _ = self._run(observation, keep=False)
     return out, network_state
 
+  def pairs_with(self, other):
+    """True when `other` has this network's layer sequence (a target copy), so that
+    `forward_pair` can fuse the two forward passes layer by layer."""
+    if type(other) is not type(self) or not getattr(other, '_built', False) or not self._built:
+      return False
+    mine = [l for l in self._layers if not isinstance(l, layers_lib.CastScale)]
+    theirs = [l for l in other._layers if not isinstance(l, layers_lib.CastScale)]
+    return len(mine) == len(theirs) and all(type(a) is type(b) for a, b in zip(mine, theirs))
+
+  def forward_pair(self, other, observation, other_observation, keep=True):
+    """`self.forward_train(observation)` and `other(other_observation)` with every layer pair
+    issued as ONE launch where the kernels support it (DqnAgent: online network on obs[:, 0],
+    target network on obs[:, T-1]).  Returns ((out, tape), other_out)."""
+    self._require_built()
+    other._require_built()
+    tape = []
+    x, x2 = observation, other_observation
+    theirs = [l for l in other._layers if not isinstance(l, layers_lib.CastScale)]
+    mine = [l for l in self._layers if not isinstance(l, layers_lib.CastScale)]
+    for l, l2 in zip(mine, theirs):
+      if hasattr(l, 'forward_pair'):
+        y, y2 = l.forward_pair(l2, x, x2)
+      else:
+        y, y2 = l.forward(x), l2.forward(x2)
+      if keep:
+        tape.append((l, x, y))
+      x, x2 = y, y2
+    return (x, tape), x2
+
   def forward_train(self, observation):
     """Forward that records activations; returns (output, tape)."""
     return self._run(observation, keep=True)

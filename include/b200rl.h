@@ -372,6 +372,15 @@ int b200rl_tc2_trace_buffer(long long* dev_buf);
 int b200rl_dense_fwd(const float* X, int64_t ldx, const float* W, const float* bias, float* Y,
                      int64_t M, int64_t K, int64_t N, int act, void* workspace,
                      int64_t ws_bytes, void* stream);
+/* Two dense layers of identical shape (X1 @ W1 + b1 -> Y1, X2 @ W2 + b2 -> Y2; biases both given
+ * or both NULL) in ONE launch of the persistent tensor-core kernel; two launches when that kernel
+ * does not take the shape.  DqnAgent evaluates the online network on obs[:, 0] and the target
+ * network on obs[:, T-1] this way (agents/dqn/dqn_agent.py:488-520, :575-579 in the reference are
+ * the two independent forward passes).  Workspace as b200rl_dense_fwd (split-K needs room for both). */
+int b200rl_dense_fwd_pair(const float* X1, const float* X2, int64_t ldx, const float* W1,
+                          const float* W2, const float* bias1, const float* bias2, float* Y1,
+                          float* Y2, int64_t M, int64_t K, int64_t N, int act, void* workspace,
+                          int64_t ws_bytes, void* stream);
 /* Given dY[M,N] (already multiplied by act'), compute dX[M,K] (optional, NULL to skip),
  * dW[K,N] (optional) and db[N] (optional).  accumulate!=0 adds into dW/db instead of
  * overwriting.  x_act: activation code of the layer whose OUTPUT is X (B200RL_ACT_NONE when X is
@@ -398,6 +407,11 @@ typedef struct {
 int b200rl_conv2d_fwd(const void* X, int x_is_u8, float x_scale, const float* Wt,
                       const float* bias, float* Y, const b200rl_conv_t* g, int act,
                       void* workspace, int64_t ws_bytes, void* stream);
+/* Two convolutions of identical geometry in one launch (see b200rl_dense_fwd_pair). */
+int b200rl_conv2d_fwd_pair(const void* X1, const void* X2, int x_is_u8, float x_scale,
+                           const float* Wt1, const float* Wt2, const float* bias1,
+                           const float* bias2, float* Y1, float* Y2, const b200rl_conv_t* c,
+                           int act, void* workspace, int64_t ws_bytes, void* stream);
 /* dX, dW and db may each be NULL (that gradient is skipped), so the parameter gradients and the
  * input gradient of one layer can be issued on different streams.  x_act as in
  * b200rl_dense_bwd: the col2im scatter-add is linear, so act'(X) is applied to every
