@@ -125,4 +125,4 @@ class DqnTorchOracle(object):
             tg.copy_(s)
           else:
             tg.mul_(1 - self.tau).add_(self.tau * s)
-    return float(loss)
+    return float(loss.detach())
