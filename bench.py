@@ -283,6 +283,8 @@ def main():
   ap.add_argument('--no-cpu-baseline', action='store_true')
   ap.add_argument('--no-graph', action='store_true')
   ap.add_argument('--no-extra', action='store_true', help='skip configs 1/3/4/5 and dp_parity')
+  ap.add_argument('--extras-timeout', type=float, default=600.0,
+                  help='seconds the extra configs + CPU arm may take before the line is printed without them')
   ap.add_argument('--no-prefetch', action='store_true',
                   help='sample and train back to back on one stream (default: the sample of step '
                        'i+1 runs on a side stream beside train(i), like dataset.prefetch(1))')
@@ -327,10 +329,10 @@ def main():
   def guarded(name, fn):
     try:
       extra[name] = fn()
+      torch.cuda.synchronize()
     except Exception as e:  # pylint: disable=broad-except
       extra[name] = dict(error=f'{type(e).__name__}: {e}')
       sys.stderr.write(f'[rank {rank}] {name} failed: {type(e).__name__}: {e}\n')
-    torch.cuda.synchronize()
 
   # ---- data-parallel parity first (small, eager; uses the process group before any graph) -------
   if world > 1 and not args.no_extra:
@@ -656,30 +658,7 @@ def main():
   e2e_value = Ke / (e2e_ms / 1000.0) * world
   assert len(losses_read) == Ke and all(np.isfinite(losses_read)), 'e2e loss read-back incomplete'
 
-  # ---- the other BASELINE configs (ring freed first: config 5 needs the HBM) --------------------
-  del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only, e2e_fns
-  del sample_bufs, bodies
-  if use_graph:
-    del fn
-    if prefetch:
-      del graphs
-  torch.cuda.empty_cache()
-  if not args.no_extra:
-    from profiles import configs
-    guarded('gather_sweep', lambda: configs.gather_sweep(
-        dev, world, rank, peaks, caps_m=(1, 2, 4) if world == 1 else ((1, 4, 8) if world == 2 else (1, 4, 8, 16))))
-    guarded('ppo_update', lambda: configs.ppo_update(strategy, dev, peaks))
-    guarded('sac_step', lambda: configs.sac_step(strategy, dev, peaks))
-    if world == 1:
-      guarded('cartpole_iter', lambda: configs.cartpole_iter(dev))
-
-  cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu_baseline:
-    arm = CpuArm()
-    sps, sweep, sample = arm.measure(8, 3)
-    cpu = dict(value=sps, unit='steps/s', cores=arm.threads, kind='port', sample=sample,
-               other_thread_counts=sweep, logical_cpus=os.cpu_count())
-
+  line = None
   if rank == 0:
     line = dict(
         metric='train steps/sec (DQN Atari-shape, batch 256)', value=value, unit='steps/s',
@@ -721,13 +700,70 @@ def main():
         final_loss=final_loss)
     if parity is not None:
       line['parity'] = parity
-    if cpu is not None:
-      line['cpu_baseline'] = cpu
-    line.update(extra)
-    print(json.dumps(line), flush=True)
+
+  # The main measurement is complete: everything below (configs 1 / 3 / 4 / 5, the CPU arm) only
+  # ADDS keys to the line.  A watchdog makes sure the line is printed even if one of them hangs
+  # (e.g. a rank lost inside a collective at an untested world size): on expiry rank 0 prints what
+  # it has and every rank leaves.
+  import threading
+  printed = threading.Lock()
+
+  def emit(note=None):
+    if not printed.acquire(blocking=False):
+      return
+    if rank == 0:
+      out = dict(line)
+      out.update(extra)
+      if note:
+        out['extras_note'] = note
+      print(json.dumps(out), flush=True)
+
+  def on_timeout():
+    sys.stderr.write(f'[rank {rank}] extras exceeded {args.extras_timeout} s; printing the line without them\n')
+    emit(f'watchdog: extras did not finish within {args.extras_timeout} s')
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+  watchdog = threading.Timer(args.extras_timeout + (0 if rank == 0 else 5), on_timeout)
+  watchdog.daemon = True
+  watchdog.start()
+
+  # ---- the other BASELINE configs (ring freed first: config 5 needs the HBM) --------------------
+  del rb, st_store, obs_store, act_store, nst_store, rew_store, disc_store, exp, staged, train_only, e2e_fns
+  del sample_bufs, bodies
+  if use_graph:
+    del fn
+    if prefetch:
+      del graphs
+  torch.cuda.empty_cache()
+  if not args.no_extra:
+    from profiles import configs
+    guarded('gather_sweep', lambda: configs.gather_sweep(
+        dev, world, rank, peaks, caps_m=(1, 2, 4) if world == 1 else ((1, 4, 8) if world == 2 else (1, 4, 8, 16))))
+    guarded('ppo_update', lambda: configs.ppo_update(strategy, dev, peaks))
+    guarded('sac_step', lambda: configs.sac_step(strategy, dev, peaks))
+    if world == 1:
+      guarded('cartpole_iter', lambda: configs.cartpole_iter(dev))
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    arm = CpuArm()
+    sps, sweep, sample = arm.measure(8, 3)
+    cpu = dict(value=sps, unit='steps/s', cores=arm.threads, kind='port', sample=sample,
+               other_thread_counts=sweep, logical_cpus=os.cpu_count())
+
+  if cpu is not None and line is not None:
+    line['cpu_baseline'] = cpu
+  watchdog.cancel()
+  emit()
   if world > 1:
     # CUDA graphs that captured NCCL kernels make the communicator teardown hang on this stack:
-    # leave without running destructors once every rank is done.
+    # leave without running destructors once every rank is done (or after a minute, if a rank
+    # never arrives).
+    leave = threading.Timer(60.0, lambda: os._exit(0))
+    leave.daemon = True
+    leave.start()
     dist.barrier()
     torch.cuda.synchronize()
     sys.stdout.flush()
