@@ -200,9 +200,9 @@ class Table(object):
           'Table {!r} is a queue of {} items and is full; dm-reverb would block the writer until '
           'an item is sampled.'.format(self.name, self._rate_limiter.max_size))
     store.retain(rows)
-    while len(self._dense) >= self._max_size:
-      self._drop(self._victim())
     self._put(_Item(key, priority, rows, store))
+    while len(self._dense) > self._max_size:     # the remover also sees the new item, as in Reverb
+      self._drop(self._victim())
 
   def reset(self):
     for item in list(self._dense):
@@ -333,13 +333,15 @@ class HbmStepStore(object):
 class _RowPool(object):
   """Row allocation, reference counts and append staging in front of a step store."""
 
-  def __init__(self, store):
+  def __init__(self, store, specs):
     self._store = store
+    self.store_specs = specs
     self._refs = np.zeros(store.capacity, np.int32)
     self._free = list(range(store.capacity - 1, -1, -1))
     self._pending_rows = np.zeros(store.stage, np.int64)
     self._n_pending = 0
-    self._dtypes = None
+    self._pending = set()         # rows staged but not yet written
+    self._deferred = []           # rows that died while staged: reusable after the flush
 
   @property
   def store(self):
@@ -360,6 +362,7 @@ class _RowPool(object):
     for buf, leaf in zip(bufs, flat_step):
       buf[i] = leaf
     self._pending_rows[i] = row
+    self._pending.add(row)
     self._n_pending = i + 1
     if self._n_pending == self._store.stage:
       self.flush()
@@ -369,6 +372,9 @@ class _RowPool(object):
     if self._n_pending:
       self._store.commit(self._pending_rows, self._n_pending)
       self._n_pending = 0
+      self._pending.clear()
+      self._free.extend(self._deferred)
+      del self._deferred[:]
 
   def retain(self, rows):
     np.add.at(self._refs, rows, 1)
@@ -377,9 +383,11 @@ class _RowPool(object):
     np.subtract.at(self._refs, rows, 1)
     rows = np.unique(rows)
     dead = rows[self._refs[rows] == 0]
-    if dead.size:
-      # a staged-but-unflushed step that dies is written anyway; its row is simply reused later
-      self._free.extend(int(r) for r in dead)
+    for r in dead:
+      # a row that dies while still staged must not be handed out again before the flush: one
+      # write launch would then carry two values for the same row
+      r = int(r)
+      (self._deferred if r in self._pending else self._free).append(r)
 
   def read(self, rows):
     self.flush()
@@ -413,7 +421,15 @@ class _Column(object):
     return _ColumnRef(self._writer, self._leaf, start, max(start, stop))
 
 
-_ColumnRef = collections.namedtuple('_ColumnRef', ['writer', 'leaf', 'start', 'stop'])
+class _ColumnRef(object):
+  """Steps [start, stop) of one column of a writer's episode (a nest LEAF, hence not a tuple)."""
+  __slots__ = ('writer', 'leaf', 'start', 'stop')
+
+  def __init__(self, writer, leaf, start, stop):
+    self.writer, self.leaf, self.start, self.stop = writer, leaf, start, stop
+
+  def __len__(self):
+    return self.stop - self.start
 
 
 class TrajectoryWriter(object):
@@ -556,8 +572,7 @@ class Server(object):
     if pool is None:
       specs = [tensor_spec.TensorSpec(shape, np.dtype(dt), 'leaf%d' % i)
                for i, (dt, shape) in enumerate(leaves)]
-      pool = _RowPool(self._store_factory(specs, self._cap0))
-      pool.store_specs = specs
+      pool = _RowPool(self._store_factory(specs, self._cap0), specs)
       self._pools[sig] = pool
     return pool
 
@@ -613,6 +628,10 @@ class Client(object):
 
   def mutate_priorities(self, table, updates=None, deletes=None):
     self._server._table(table).mutate(updates, deletes)
+
+  def update_priorities(self, table, keys, priorities):
+    """reverb.TFClient.update_priorities: parallel arrays of keys and new priorities."""
+    self.mutate_priorities(table, updates={int(k): float(p) for k, p in zip(keys, priorities)})
 
   def sample(self, table, num_samples=1):
     """Yields `ReplaySample(info, data)` with `data` a nest of `[T, ...]` device tensors."""
