@@ -8,16 +8,27 @@ from agents_b200.networks import q_network
 from agents_b200.networks import sequential
 from agents_b200.specs import tensor_spec
 from oracle import nn as onn
+from conftest import record_parity
 
 pytestmark = pytest.mark.gpu
 f32 = np.float32
 
 
-def _close(got, want, rtol=2e-5, atol=None):
+def _close(got, want, rtol=2e-5, atol=None, tag=None):
+  """Forward outputs: 2e-5 elementwise.  Gradients (`tag` given) are sums of up to 70 001 products of
+  both signs: numpy sums them pairwise, the kernels in K-tile order with split-K / col2im atomics, and
+  3xTF32 drops the lo*lo term (2^-22 per product), so single ELEMENTS of a cancelling sum differ by
+  up to ~1e-4 of their own value while the error relative to the largest element stays near 1e-6;
+  that figure is recorded per tag (gpurun_out/parity_measured.json -> profiles/) and the loss-level
+  1e-5 bound of the north star is asserted in tests/test_baseline_parity_gpu.py."""
   want = np.asarray(want)
   if atol is None:
     atol = 2e-6 * max(1.0, float(np.abs(want).max()))
-  np.testing.assert_allclose(got.cpu().numpy(), want, rtol=rtol, atol=atol)
+  got = got.cpu().numpy()
+  if tag is not None:
+    record_parity('nn_layers_err_rel_to_max', **{
+        tag: float(np.abs(got - want).max()) / max(float(np.abs(want).max()), 1e-30)})
+  np.testing.assert_allclose(got, want, rtol=rtol, atol=atol)
 
 
 def _net_and_oracle(cuda, layers, input_shape, in_dtype=torch.float32):
@@ -54,11 +65,11 @@ def test_dense_fwd_bwd(cuda, M, K, N, act):
   net.backward(tape, torch.as_tensor(dy, device=cuda))
   wg = orc.backward(wtape, dy)
   lay = net.layers[0]
-  _close(lay.d_kernel, wg[0], rtol=1e-4)
-  _close(lay.d_bias, wg[1], rtol=1e-4)
+  _close(lay.d_kernel, wg[0], rtol=1e-4, tag='dense_dW')
+  _close(lay.d_bias, wg[1], rtol=1e-4, tag='dense_db')
   dx = lay.backward(torch.as_tensor(x, device=cuda), y, torch.as_tensor(dy, device=cuda), need_dx=True)
   wdz = onn.act_bwd(wy, dy, act)
-  _close(dx, wdz @ orc.layers[0]['w'].T, rtol=1e-4)
+  _close(dx, wdz @ orc.layers[0]['w'].T, rtol=1e-4, tag='dense_dX')
 
 
 def test_dense_strided_batch_input(cuda):
@@ -73,7 +84,7 @@ def test_dense_strided_batch_input(cuda):
     dy = rng.randn(B, N).astype(f32)
     net.backward(tape, torch.as_tensor(dy, device=cuda))
     _, wtape = orc.forward(x[:, t], keep=True)
-    _close(net.layers[0].d_kernel, orc.backward(wtape, dy)[0], rtol=1e-4)
+    _close(net.layers[0].d_kernel, orc.backward(wtape, dy)[0], rtol=1e-4, tag='dense_dW')
 
 
 @pytest.mark.parametrize('N,H,W,C,F,ks,st,u8', [
@@ -94,13 +105,13 @@ def test_conv_fwd_bwd(cuda, N, H, W, C, F, ks, st, u8):
   dy = rng.randn(*wy.shape).astype(f32)
   net.backward(tape, torch.as_tensor(dy, device=cuda))
   wg = orc.backward(wtape, dy)
-  _close(conv.d_kernel, wg[0], rtol=1e-4)
-  _close(conv.d_bias, wg[1], rtol=1e-4)
+  _close(conv.d_kernel, wg[0], rtol=1e-4, tag='conv_dW')
+  _close(conv.d_bias, wg[1], rtol=1e-4, tag='conv_db')
   if not u8:
     dx = conv.backward(torch.as_tensor(x, device=cuda), y, torch.as_tensor(dy, device=cuda), need_dx=True)
     wdz = onn.act_bwd(wy, dy, 'relu')
     wdx, _, _ = onn.conv2d_bwd(x, orc.layers[0]['w'], wdz, st)
-    _close(dx, wdx, rtol=1e-4)
+    _close(dx, wdx, rtol=1e-4, tag='conv_dX')
 
 
 def test_conv_strided_batch_u8(cuda):
@@ -142,7 +153,7 @@ def test_mnih_q_network_forward_backward(cuda):
   net.backward(tape, torch.as_tensor(dq, device=cuda))
   wg = orc.backward(wtape, dq)
   for g, w in zip(net._grad_views, wg):
-    _close(g, w, rtol=2e-4)
+    _close(g, w, rtol=2e-4, tag='mnih_net_grads_b8')   # 4 layers deep: errors of the dX chain compound
 
 
 def test_forward_pair_matches_separate_forwards(cuda):
@@ -171,4 +182,4 @@ def test_forward_pair_matches_separate_forwards(cuda):
   dq = torch.randn(64, 6, device=cuda, generator=g)
   g_pair = online.backward(tape, dq).clone()
   g_ref = online.backward(tape_ref, dq).clone()
-  _close(g_pair, g_ref.cpu().numpy(), rtol=1e-4)
+  _close(g_pair, g_ref.cpu().numpy(), rtol=1e-4, tag='paired_vs_separate_grads')   # two atomic orders
