@@ -475,6 +475,10 @@ class TrajectoryWriter(object):
           data, [_Column(self, i) for i in range(len(flat))]) if nest.is_nested(data) else _Column(self, 0)
     elif len(flat) != len(self._pool.store_specs):
       raise ValueError('append: the step does not match the structure of earlier steps.')
+    for a, spec in zip(flat, self._pool.store_specs):
+      if tuple(a.shape) != tuple(spec.shape):      # numpy would silently broadcast a smaller leaf
+        raise ValueError('append: leaf {!r} has shape {}, the step store holds {}.'.format(
+            spec.name, tuple(a.shape), tuple(spec.shape)))
     self._episode_rows.append(self._pool.append(flat))
     # keep-alive window: the writer's own reference on steps older than `keep` is dropped
     limit = len(self._episode_rows) - self._keep
