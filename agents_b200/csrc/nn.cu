@@ -1144,7 +1144,7 @@ static int launch_tc2_cfg(const AL& a, const BL& b, const GemmArgs& g, const tc:
   // epilogue-bound shapes (col2im scatter-add, short K loops) get all eight epilogue warps
   static const int epi_env = [] { const char* e = getenv("B200RL_TC2_EPI_WARPS"); return e ? atoi(e) : 0; }();
   const int epi_warps = (epi_env == 4 || epi_env == 8) ? epi_env
-                        : (EPI == tc::EPI_COL2IM || kps <= 224) ? 8 : 4;
+                        : (EPI == tc::EPI_COL2IM || EPI == tc::EPI_COL2IM_MERGE || kps <= 224) ? 8 : 4;
   // dynamic work distribution (b200rl_set_tile_scheduler) when a CTA has more than one item
   static int sched_seq = 0;
   int sched_slot = -1;
@@ -1653,8 +1653,16 @@ int b200rl_conv2d_bwd(const void* X, int x_is_u8, float x_scale, const float* Wt
     epi.mask = mask;
     const ARow da{dY, F};
     const BCol db_{Wt, F};
+    // neighbour pre-sum of the col2im epilogue (tc2_gemm.cuh): the partner column group sits
+    // stride * C = 64 columns away, i.e. in the other half of the same 128-column tile (the Mnih
+    // conv2 (k4 s2 C32) and conv3 (k3 s1 C64) input gradients); B200RL_COL2IM_MERGE=0 turns it off
+    static const int merge_env = [] { const char* e = getenv("B200RL_COL2IM_MERGE"); return e ? atoi(e) : 1; }();
+    if (merge_env && (int64_t)c->stride * c->C == 64 && (c->C & 15) == 0 && cg.OW > 1) epi.merge_cols = 64;
     if (use_tc2(da, db_, g)) {
-      if (gemm_mode() == 2) rc = launch_tc2_cfg<128, 1, tc::EPI_COL2IM>(da, db_, g, epi);
+      if (epi.merge_cols) {
+        if (gemm_mode() == 2) rc = launch_tc2_cfg<128, 1, tc::EPI_COL2IM_MERGE>(da, db_, g, epi);
+        else rc = launch_tc2_cfg<128, 3, tc::EPI_COL2IM_MERGE>(da, db_, g, epi);
+      } else if (gemm_mode() == 2) rc = launch_tc2_cfg<128, 1, tc::EPI_COL2IM>(da, db_, g, epi);
       else rc = launch_tc2_cfg<128, 3, tc::EPI_COL2IM>(da, db_, g, epi);
     } else if (gemm_mode() == 2) rc = launch_tc_cfg<128, 3, 1, tc::EPI_COL2IM>(da, db_, g, epi);
     else rc = launch_tc_cfg<128, 3, 3, tc::EPI_COL2IM>(da, db_, g, epi);

@@ -41,6 +41,7 @@ namespace tc2 {
 using tc::EpiArgs;
 using tc::EPI_ATOMIC;
 using tc::EPI_COL2IM;
+using tc::EPI_COL2IM_MERGE;
 using tc::EPI_STORE;
 using tc::kBK;
 using tc::kBM;
@@ -146,6 +147,13 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
         "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]),
         "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+        "=r"(r[7])
       : "r"(taddr));
 }
 // one out-of-line body instead of 16 inlined tanhf expansions per epilogue step
@@ -783,8 +791,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       float* cbase = nullptr;
       const float* ybase = nullptr;
       int64_t wc = 0;
-      if (EPI == EPI_COL2IM && m < M) {
-        uint32_t img, rem, oy, ox;
+      uint32_t ox = 0;
+      if ((EPI == EPI_COL2IM || EPI == EPI_COL2IM_MERGE) && m < M) {
+        uint32_t img, rem, oy;
         epi.g.d_ohow.divmod((uint32_t)m, img, rem);
         epi.g.d_ow.divmod(rem, oy, ox);
         wc = (int64_t)epi.g.W * epi.g.C;
@@ -792,6 +801,111 @@ __global__ void __launch_bounds__(kThreads, 1)
         cbase = epi.dx + (int64_t)img * epi.g.H * wc + in_off;
         if (epi.mask.y) ybase = epi.mask.y + (int64_t)img * epi.mask.ld + in_off;
       }
+      if constexpr (EPI == EPI_COL2IM_MERGE) {
+        // Neighbour pre-sum.  Output positions (oy, ox) and (oy, ox + 1) are consecutive rows m,
+        // i.e. consecutive TMEM lanes, and patch column (ky, kx, ch) of the first addresses the same
+        // input element as column (ky, kx - stride, ch) of the second: merge_cols = stride * C = 64
+        // columns to the left, the other half of this 128-column tile.  Each warp therefore drains
+        // a 16-column chunk of the low half together with its partner chunk of the high half, adds
+        // its right neighbour's low values to its own high values with one shuffle per column, and
+        // issues the low-half red only where no left neighbour took it (lane 0 of the warp, first
+        // column of an image row): ~1.14 instead of 2 red.global.add.v4 per pair of 4-channel
+        // groups for a 9-wide output.  act'(y) depends on the target only, so it is applied to
+        // the merged sum.  The summation order of dX was never fixed (atomics).
+        const bool row_ok = m < M;
+        const bool take = row_ok && lane < 31 && m + 1 < M && ox + 1 < (uint32_t)epi.g.OW;
+        const bool given = row_ok && lane > 0 && ox > 0;
+        const uint32_t kwc = (uint32_t)(epi.g.KW * epi.g.C), wc32 = (uint32_t)wc;
+        const int kLowPerWarp = 64 / (epi_warps >> 2);
+        // accumulator columns [c, c + 8) of this lane's row (the two column sets of the WIDE layout
+        // added); 8 instead of 16 columns per tcgen05.ld keeps the live set of the merged pass
+        // within the register cap of an 800-thread CTA
+        auto load8 = [&](int c, uint32_t (&r)[8]) {
+          const uint32_t taddr =
+              tmem_base + ((uint32_t)(q * 32) << 16) + buf * L::kAccCols + (uint32_t)c;
+          tmem_ld8(taddr, r);
+          if (kWide) {
+            uint32_t r2[8];
+            tmem_ld8(taddr + BN, r2);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
+          } else {
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          }
+        };
+        auto red4 = [&](uint32_t off, float4 v) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + off),
+                       "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                       : "memory");
+        };
+        auto masked = [&](float4 y, float4 v) {
+          v.x = dact(y.x, v.x, epi.mask.act); v.y = dact(y.y, v.y, epi.mask.act);
+          v.z = dact(y.z, v.z, epi.mask.act); v.w = dact(y.w, v.w, epi.mask.act);
+          return v;
+        };
+#pragma unroll 1
+        for (int c = chalf * kLowPerWarp; c < (chalf + 1) * kLowPerWarp; c += 16) {
+          const uint32_t nb_lo = (uint32_t)wk.n0 + (uint32_t)c, nb_hi = nb_lo + 64u;
+          if (nb_lo >= (uint32_t)N) break;         // N % 16 == 0: a chunk is all in or all out
+          const bool hi_ok = nb_hi < (uint32_t)N;  // uniform over the warp
+          uint32_t ky_lo, rr_lo;
+          epi.g.d_kwc.divmod(nb_lo, ky_lo, rr_lo);
+          const bool merge = hi_ok && rr_lo + 64u < kwc;   // partner chunk in the same ky row
+          const bool need_lo = row_ok && !(merge && given);
+          const bool need_hi = row_ok && hi_ok;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {            // 8 columns (two 4-channel groups) at a time
+            // patch column -> (ky, kx * C + ch) -> offset into dX / the act' mask; the mask loads of
+            // both chunks are issued BEFORE the accumulator reads so that their latency overlaps the
+            // tcgen05.ld round trips and the shuffles (run 22: with one dependent load per group the
+            // saved atomics were paid back in load latency)
+            uint32_t off_lo[2], off_hi[2];
+            float4 y_lo[2], y_hi[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint32_t ky, rr;
+              epi.g.d_kwc.divmod(nb_lo + (uint32_t)(8 * h + 4 * j), ky, rr);
+              off_lo[j] = ky * wc32 + rr;
+              epi.g.d_kwc.divmod(nb_hi + (uint32_t)(8 * h + 4 * j), ky, rr);
+              off_hi[j] = ky * wc32 + rr;
+              if (ybase && need_lo) y_lo[j] = *reinterpret_cast<const float4*>(ybase + off_lo[j]);
+              if (ybase && need_hi) y_hi[j] = *reinterpret_cast<const float4*>(ybase + off_hi[j]);
+            }
+            uint32_t lo[8];
+            load8(c + 8 * h, lo);
+            float t[8];                            // the right neighbour's low values
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float nbr = __shfl_down_sync(0xffffffffu, __uint_as_float(lo[j]), 1);
+              t[j] = (merge && take) ? nbr : 0.f;
+            }
+            if (need_lo) {                         // (before the partner read: lo / y_lo die here)
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                float4 v = make_float4(__uint_as_float(lo[4 * j]), __uint_as_float(lo[4 * j + 1]),
+                                       __uint_as_float(lo[4 * j + 2]), __uint_as_float(lo[4 * j + 3]));
+                if (ybase) v = masked(y_lo[j], v);
+                red4(off_lo[j], v);
+              }
+            }
+            uint32_t hi[8];
+            if (hi_ok) load8(c + 64 + 8 * h, hi);
+            if (need_hi) {
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                float4 v = make_float4(__uint_as_float(hi[4 * j]) + t[4 * j],
+                                       __uint_as_float(hi[4 * j + 1]) + t[4 * j + 1],
+                                       __uint_as_float(hi[4 * j + 2]) + t[4 * j + 2],
+                                       __uint_as_float(hi[4 * j + 3]) + t[4 * j + 3]);
+                if (ybase) v = masked(y_hi[j], v);
+                red4(off_hi[j], v);
+              }
+            }
+          }
+        }
+      } else {
 #pragma unroll 1
       for (int c = chalf * kColsPerWarp; c < (chalf + 1) * kColsPerWarp; c += 16) {
         uint32_t r[16];
@@ -905,6 +1019,7 @@ __global__ void __launch_bounds__(kThreads, 1)
               if (nb + j < N) dst[j] = v[j];
           }
         }
+      }
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();

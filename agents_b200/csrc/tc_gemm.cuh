@@ -295,11 +295,18 @@ __device__ __forceinline__ void scatter_tile(unsigned char* hi, unsigned char* l
 constexpr int EPI_STORE = 0;
 constexpr int EPI_COL2IM = 1;
 constexpr int EPI_ATOMIC = 2;  // C += acc with red.global.add (split-K without a reduce pass; C pre-zeroed)
+// tc2 kernel only: EPI_COL2IM with the neighbour pre-sum of EpiArgs::merge_cols (its own
+// instantiation, so that neither variant pays for the other's registers)
+constexpr int EPI_COL2IM_MERGE = 3;
 struct EpiArgs {
   ConvGeom g;
   float* dx;
   ActMask mask;     // EPI_STORE / EPI_COL2IM: multiply the input gradient by act'(mask.y)
   float* colsum;    // EPI_ATOMIC with an MN-major B view: column sums of B (bias gradient) += here
+  // EPI_COL2IM (tc2 kernel only): columns c and c + merge_cols (= stride * C) of NEIGHBOURING output
+  // positions (ox + 1, ox) address the same input element; when != 0 the epilogue adds them with a
+  // lane shuffle before the red.global.add (see tc2_gemm.cuh).  0: every column group is scattered.
+  int merge_cols;
 };
 
 // AL / BL are the fp32 operand views of nn.cu (row index = m for A, n for B).
