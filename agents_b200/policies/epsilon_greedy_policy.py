@@ -1,2 +1,33 @@
-"""Module alias matching tf_agents/policies/epsilon_greedy_policy.py; see q_policy.py in this package."""
-from agents_b200.policies.q_policy import *  # noqa: F401,F403
+"""EpsilonGreedyPolicy: where(u >= epsilon, greedy action, uniform random allowed action).
+
+Reference: policies/epsilon_greedy_policy.py:120-145 (`u ~ U[0, 1)` per batch row, the random
+branch is `RandomTFPolicy` over the same action mask).  Device work: one b200rl_epsilon_greedy
+launch (greedy_policy._Selecting).  `epsilon` may be a float or a callable evaluated on the host at
+every call (:93-99).
+"""
+from agents_b200.policies.greedy_policy import _Selecting
+from agents_b200.trajectories import policy_step
+
+
+class EpsilonGreedyPolicy(_Selecting):
+  """where(u >= epsilon, greedy, uniform random) (epsilon_greedy_policy.py:120-145)."""
+
+  def __init__(self, policy, epsilon, seed=0, name=None):
+    super().__init__(policy.time_step_spec, policy.action_spec, seed=seed, name=name)
+    self._wrapped_policy = policy
+    self._epsilon = epsilon
+
+  @property
+  def wrapped_policy(self):
+    return self._wrapped_policy
+
+  def variables(self):
+    return self._wrapped_policy.variables()
+
+  def _get_epsilon(self):
+    return self._epsilon() if callable(self._epsilon) else self._epsilon
+
+  def _action(self, time_step, policy_state, seed):
+    q, mask = self._wrapped_policy.q_values(time_step)
+    act = self._select(q, mask, self._get_epsilon(), self._wrapped_policy._action_dtype)
+    return policy_step.PolicyStep(act, policy_state, ())

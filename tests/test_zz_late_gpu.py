@@ -81,13 +81,13 @@ def test_py_driver_feeds_the_ring(cuda):
   (dynamic_step_driver_test.py:121-166)."""
   from agents_b200.drivers import py_driver
   from agents_b200.environments import batched_py_environment
-  from agents_b200.policies import py_policy
+  from agents_b200.policies import py_tf_eager_policy
   from agents_b200.replay_buffers import tf_uniform_replay_buffer as rb_mod
   from py_env_mocks import PyEnvironmentMock
   from test_driver_gpu import PolicyMock
   env = batched_py_environment.BatchedPyEnvironment([PyEnvironmentMock()], multithreading=False)
   device_policy = PolicyMock(env.time_step_spec(), env.action_spec(), cuda)
-  policy = py_policy.PyTFEagerPolicy(device_policy, device=cuda)
+  policy = py_tf_eager_policy.PyTFEagerPolicy(device_policy, device=cuda)
   rb = rb_mod.TFUniformReplayBuffer(device_policy.trajectory_spec, batch_size=1, max_length=1000, device=cuda)
   driver = py_driver.PyDriver(env, policy, observers=[py_driver.PinnedAddBatch(rb)], max_steps=6)
   driver.run(env.reset(), policy.get_initial_state(1))
