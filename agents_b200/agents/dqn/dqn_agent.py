@@ -218,6 +218,12 @@ class DqnAgent(tf_agent.TFAgent):
       (q, _), tape = self._q_network(obs0), None
     if side is not None:
       main.wait_stream(side)
+      if not torch.cuda.is_current_stream_capturing():
+        # eager fork (B200RL_DQN_OVERLAP=2): these tensors were allocated on the side stream and
+        # are consumed on the main one; tell the caching allocator before they can be recycled
+        next_t.record_stream(main)
+        if next_sel is not next_t:
+          next_sel.record_stream(main)
     elif self._overlap_target and not torch.cuda.is_current_stream_capturing():
       workspace.mirror(q.device, 1)   # size the side-stream scratch for a later capture
     return self._td(exp, B, T, q, next_t, next_sel, next_mask, weights, tape)
