@@ -589,3 +589,70 @@ def test_dead_staged_rows_wait_for_the_flush():
   sample, _ = next(iter(replay.as_dataset(sample_batch_size=1)))
   assert int(sample[0, 0]) == 19
   assert srv.test_stores[0].commits >= 1
+
+
+def test_mutate_priorities_deletes_and_client_sample():
+  table = reverb.Table('m', sampler=reverb.selectors.Prioritized(0.5), remover=reverb.selectors.Lifo(),
+                       max_size=4, rate_limiter=reverb.rate_limiters.MinSize(1))
+  srv = _server([table])
+  client = srv.localhost_client()
+  replay = _scalar_replay(table, srv)
+  _write_scalars(replay, table.name, 6, priority=lambda i: 1 + i)
+  # Lifo remover: every insert beyond max_size evicts the newest item, i.e. the one just written
+  assert sorted(int(it.priority) for it in table._dense) == [1, 2, 3, 4]
+  keys = {int(it.priority): it.key for it in table._dense}
+  client.mutate_priorities(table.name, updates={keys[1]: 0.0, keys[2]: 0.0, 12345: 9.0},
+                           deletes=[keys[3], 999])
+  assert table.current_size == 3 and srv.live_rows() == 3
+  samples = list(client.sample(table.name, num_samples=20))
+  assert len(samples) == 20
+  assert all(int(s.data[0][0]) == 3 for s in samples)          # value 3 carries priority 4
+  assert all(s.info.probability == pytest.approx(1.0) for s in samples)
+  assert srv.live_rows() == 3                                    # reader pins were released
+  client.update_priorities(table.name, [keys[1]], [7.0])
+  seen = {int(s.data[0][0]) for s in client.sample(table.name, num_samples=200)}
+  assert seen == {0, 3}
+
+
+def test_prioritized_all_zero_priorities_sample_uniformly():
+  table = reverb.Table('z', sampler=reverb.selectors.Prioritized(1.0), remover=reverb.selectors.Fifo(),
+                       max_size=10, rate_limiter=reverb.rate_limiters.MinSize(1))
+  replay = _scalar_replay(table, _server([table]))
+  _write_scalars(replay, table.name, 4, priority=lambda i: 0)
+  it = iter(replay.as_dataset(sample_batch_size=1))
+  assert {int(next(it)[0][0, 0]) for _ in range(200)} == {0, 1, 2, 3}
+
+
+def test_uniform_remover_keeps_the_size_bound():
+  table = reverb.Table('u', sampler=reverb.selectors.Uniform(), remover=reverb.selectors.Uniform(),
+                       max_size=5, rate_limiter=reverb.rate_limiters.MinSize(1))
+  srv = _server([table])
+  replay = _scalar_replay(table, srv)
+  _write_scalars(replay, table.name, 60)
+  assert table.current_size == 5 and srv.live_rows() == 5
+  assert len({it.key for it in table._dense}) == 5
+
+
+def test_two_step_structures_get_two_stores():
+  """Writers with differently shaped steps share the server but not a step store."""
+  t1, t2 = _uniform_table('a'), _uniform_table('b')
+  srv = _server([t1, t2])
+  client = srv.localhost_client()
+  with client.trajectory_writer(2) as w1, client.trajectory_writer(2) as w2:
+    for i in range(3):
+      w1.append({'x': np.float32(i), 'y': np.arange(3, dtype=np.int32) + i})
+      w1.create_item('a', trajectory=nest_slice(w1.history, -1), priority=1)
+      w2.append(np.full((2, 2), i, np.uint8))
+      w2.create_item('b', trajectory=w2.history[-1:], priority=1)
+    with pytest.raises(ValueError, match='shape'):
+      w2.append(np.zeros((3,), np.uint8))
+  assert len(srv.test_stores) == 2
+  got = next(client.sample('a'))
+  assert sorted(s.name for s in srv._pools[next(iter(srv._pools))].store_specs) == ['leaf0', 'leaf1']
+  x, y = got.data                      # dict leaves come back in sorted-key order
+  assert x.dtype == np.float32 and y.shape == (1, 3) and int(y[0, 0]) == int(x[0])
+
+
+def nest_slice(history, n):
+  from agents_b200.utils import nest
+  return nest.map_structure(lambda c: c[n:], history)
