@@ -78,7 +78,10 @@ def test_row_pool_matches_model(ops, max_size, keep, times, stage):
       writer.end_episode()
       episode = []
     elif op == 'sample' and table.can_sample(1):
-      picked = table.sample(min(k, 2))
+      try:
+        picked = table.sample(min(k, 2))
+      except reverb.RateLimited:          # the first draw used up the last item (max_times_sampled)
+        picked = []
       for it, info in picked:
         np.testing.assert_array_equal(it.store.read(it.rows)[0], items[it.key])
         assert info.times_sampled >= 1
