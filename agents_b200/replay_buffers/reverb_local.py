@@ -117,6 +117,58 @@ class _Item(object):
     self.pos = -1
 
 
+class _SumTree(object):
+  """Weights of the dense item positions in a complete binary tree (numpy array, leaves in the
+  second half): `set` and `find` are O(log n), so a prioritized draw does not scan the table
+  (dm-reverb's Prioritized selector keeps the same structure)."""
+
+  def __init__(self, capacity=64):
+    self._cap = 1
+    while self._cap < capacity:
+      self._cap *= 2
+    self._t = np.zeros(2 * self._cap, np.float64)
+
+  @property
+  def total(self):
+    return float(self._t[1])
+
+  def _grow(self, n):
+    cap = self._cap
+    while cap < n:
+      cap *= 2
+    leaves = self._t[self._cap:2 * self._cap].copy()
+    self._cap = cap
+    self._t = np.zeros(2 * cap, np.float64)
+    self._t[cap:cap + leaves.shape[0]] = leaves
+    for i in range(cap - 1, 0, -1):               # rebuild the inner nodes once per doubling
+      self._t[i] = self._t[2 * i] + self._t[2 * i + 1]
+
+  def set(self, pos, weight):
+    if pos >= self._cap:
+      self._grow(pos + 1)
+    i = pos + self._cap
+    self._t[i] = weight
+    i >>= 1
+    while i >= 1:
+      self._t[i] = self._t[2 * i] + self._t[2 * i + 1]
+      i >>= 1
+
+  def get(self, pos):
+    return float(self._t[pos + self._cap]) if pos < self._cap else 0.0
+
+  def find(self, u):
+    """Position whose cumulative-weight interval contains `u` in [0, total)."""
+    i = 1
+    while i < self._cap:
+      left = self._t[2 * i]
+      if u < left:
+        i = 2 * i
+      else:
+        u -= left
+        i = 2 * i + 1
+    return i - self._cap
+
+
 class Table(object):
   """One named collection of items (reverb.Table)."""
 
@@ -135,6 +187,7 @@ class Table(object):
     self._prio = np.zeros(64, np.float64)         # priorities aligned with _dense
     self._num_unique_samples = 0
     self._server = None
+    self._tree = _SumTree() if isinstance(sampler, Prioritized) else None   # p^exponent per position
 
   @classmethod
   def queue(cls, name, max_size, signature=None):
@@ -162,20 +215,27 @@ class Table(object):
     return cap is None or self.current_size + num_inserts <= cap
 
   # -- mutation -------------------------------------------------------------------------------
+  def _set_weight(self, pos, priority):
+    self._prio[pos] = priority
+    if self._tree is not None:
+      self._tree.set(pos, float(np.power(priority, self._sampler.priority_exponent)) if priority > 0
+                     else 0.0)
+
   def _put(self, item):
     item.pos = len(self._dense)
     self._dense.append(item)
     if item.pos >= self._prio.shape[0]:
       self._prio = np.concatenate([self._prio, np.zeros_like(self._prio)])
-    self._prio[item.pos] = item.priority
+    self._set_weight(item.pos, item.priority)
     self._by_key[item.key] = item
 
   def _drop(self, item):
     last = self._dense.pop()
+    self._set_weight(len(self._dense), 0.0)       # the vacated last position
     if last is not item:
       self._dense[item.pos] = last
       last.pos = item.pos
-      self._prio[last.pos] = last.priority
+      self._set_weight(last.pos, last.priority)
     del self._by_key[item.key]
     item.store.release(item.rows)
 
@@ -213,7 +273,7 @@ class Table(object):
       item = self._by_key.get(int(key))
       if item is not None:                         # unknown keys are ignored, as in Reverb
         item.priority = float(p)
-        self._prio[item.pos] = item.priority
+        self._set_weight(item.pos, item.priority)
     for key in deletes or ():
       item = self._by_key.get(int(key))
       if item is not None:
@@ -234,13 +294,13 @@ class Table(object):
     if isinstance(s, MinHeap):
       return self._dense[int(np.argmin(self._prio[:n]))], 1.0
     if isinstance(s, Prioritized):
-      w = np.power(self._prio[:n], s.priority_exponent)
-      c = np.cumsum(w)
-      if not c[-1] > 0:                            # all priorities zero: uniform, like Reverb
+      total = self._tree.total
+      if not total > 0:                            # all priorities zero: uniform, like Reverb
         return self._dense[int(self._server.rng.integers(n))], 1.0 / n
-      i = int(np.searchsorted(c, self._server.rng.random() * c[-1], side='right'))
-      i = min(i, n - 1)
-      return self._dense[i], float(w[i] / c[-1])
+      i = self._tree.find(self._server.rng.random() * total)
+      if i >= n or not self._tree.get(i) > 0:      # rounding at an interval edge: nearest live item
+        i = int(np.argmax(self._prio[:n] > 0))
+      return self._dense[i], self._tree.get(i) / total
     raise ValueError('Unsupported sampler {!r}'.format(s))
 
   def sample(self, num_samples=1):

@@ -656,3 +656,48 @@ def test_two_step_structures_get_two_stores():
 def nest_slice(history, n):
   from agents_b200.utils import nest
   return nest.map_structure(lambda c: c[n:], history)
+
+
+def test_prioritized_sum_tree_tracks_inserts_evictions_and_updates():
+  """The sampler's sum tree holds p^exponent at every live dense position and 0 elsewhere through
+  growth past its initial 64 leaves, FIFO evictions (swap-remove), priority updates and deletes;
+  draws follow p^exponent / sum."""
+  alpha = 0.7
+  table = reverb.Table('p', sampler=reverb.selectors.Prioritized(alpha), remover=reverb.selectors.Fifo(),
+                       max_size=150, rate_limiter=reverb.rate_limiters.MinSize(1))
+  srv = _server([table], capacity=256)
+  replay = _scalar_replay(table, srv)
+  rng = np.random.default_rng(0)
+  prios = rng.integers(0, 6, size=400).astype(float)
+
+  def check_tree():
+    n = table.current_size
+    want = np.array([it.priority ** alpha if it.priority > 0 else 0.0 for it in table._dense])
+    got = np.array([table._tree.get(i) for i in range(n)])
+    np.testing.assert_allclose(got, want, rtol=1e-12)
+    assert all(table._tree.get(i) == 0.0 for i in range(n, n + 20))
+    assert table._tree.total == pytest.approx(want.sum(), rel=1e-9)
+
+  _write_scalars(replay, table.name, 400, priority=lambda i: prios[i])
+  assert table.current_size == 150
+  check_tree()
+  keys = [it.key for it in table._dense]
+  replay.update_priorities(np.array(keys[:40]), rng.integers(0, 9, size=40).astype(float))
+  replay.py_client.mutate_priorities(table.name, deletes=keys[40:70])
+  assert table.current_size == 120
+  check_tree()
+  # empirical distribution of 30 000 draws vs p^alpha / sum (5 sigma per item)
+  w = np.array([it.priority ** alpha if it.priority > 0 else 0.0 for it in table._dense])
+  p = w / w.sum()
+  pos = {it.key: i for i, it in enumerate(table._dense)}
+  counts = np.zeros(len(p))
+  n_draws = 30000
+  drawn = table.sample(n_draws)
+  for item, info in drawn:
+    counts[pos[item.key]] += 1
+    assert info.probability == pytest.approx(p[pos[item.key]], rel=1e-9)
+  reverb.Table.release_samples(drawn)
+  assert srv.live_rows() == table.current_size
+  sigma = np.sqrt(n_draws * p * (1 - p)) + 1e-9
+  assert np.all(np.abs(counts - n_draws * p) <= 5 * sigma + 1)
+  assert counts[p == 0].sum() == 0
