@@ -22,11 +22,13 @@ OPS = st.lists(st.tuples(st.sampled_from(['append', 'item', 'end', 'sample', 're
                          st.integers(min_value=1, max_value=4)), min_size=1, max_size=60)
 
 
-@settings(max_examples=80, deadline=None)
+@settings(max_examples=100, deadline=None)
 @given(ops=OPS, max_size=st.integers(1, 5), keep=st.integers(1, 4), times=st.sampled_from([0, 1, 2]),
-       stage=st.integers(1, 5))
-def test_row_pool_matches_model(ops, max_size, keep, times, stage):
-  table = reverb.Table('t', sampler=reverb.selectors.Uniform(), remover=reverb.selectors.Fifo(),
+       stage=st.integers(1, 5), sampler=st.sampled_from(['uniform', 'prioritized', 'fifo']))
+def test_row_pool_matches_model(ops, max_size, keep, times, stage, sampler):
+  sampler = {'uniform': reverb.selectors.Uniform(), 'prioritized': reverb.selectors.Prioritized(0.5),
+             'fifo': reverb.selectors.Fifo()}[sampler]
+  table = reverb.Table('t', sampler=sampler, remover=reverb.selectors.Fifo(),
                        max_size=max_size, max_times_sampled=times,
                        rate_limiter=reverb.rate_limiters.MinSize(1))
   stores = []
@@ -46,6 +48,12 @@ def test_row_pool_matches_model(ops, max_size, keep, times, stage):
       got = it.store.read(it.rows)[0]
       np.testing.assert_array_equal(got, items[it.key])
     assert set(items) == {it.key for it in table._dense}
+    if table._tree is not None:          # sum tree == p^0.5 at the live positions, 0 beyond them
+      n = table.current_size
+      for i, it in enumerate(table._dense):
+        assert table._tree.get(i) == pytest.approx(it.priority ** 0.5)
+      assert table._tree.get(n) == 0.0
+      assert table._tree.total == pytest.approx(sum(it.priority ** 0.5 for it in table._dense))
     # live rows = distinct steps referenced by items + the writer's keep-alive window
     (pool,) = srv._pools.values() if srv._pools else (None,)
     if pool is None:
@@ -66,7 +74,7 @@ def test_row_pool_matches_model(ops, max_size, keep, times, stage):
     elif op == 'item' and episode:
       k = min(k, len(episode), keep)
       before = {it.key for it in table._dense}
-      writer.create_item('t', trajectory=writer.history[-k:], priority=1)
+      writer.create_item('t', trajectory=writer.history[-k:], priority=(counter[0] * 7 + k) % 4)
       new = [it for it in table._dense if it.key not in before]
       for it in new:
         items[it.key] = episode[-k:]
