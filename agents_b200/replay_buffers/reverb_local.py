@@ -19,7 +19,10 @@ in which the observers hand data over — as a single-process server whose paylo
     ONE `b200rl_rb_read_rows` launch over the `[B, T]` row matrix (the same TMA bulk-copy gather
     kernel `TFUniformReplayBuffer.get_next` uses);
   * table bookkeeping (keys, priorities, FIFO order, times-sampled, removal) is host state, as it
-    is in the Reverb server.
+    is in the Reverb server; it is kept in dense numpy arrays (priority / key / times-sampled per
+    position, a sum tree for the Prioritized selector, a `[position, T]` matrix of step rows while
+    all items have one length) so that a whole batch is drawn without python work per sample
+    (`Table.sample_rows`: 0.06 ms of host time for 256 items, 19 us per appended step + item).
 
 What is deliberately different from dm-reverb: no network transport (a `Client` is bound to a
 `Server` object, or to `'localhost:<port>'` of a server of this process), no blocking rate
@@ -109,11 +112,11 @@ ReplaySample = collections.namedtuple('ReplaySample', ['info', 'data'])
 
 
 class _Item(object):
-  __slots__ = ('key', 'priority', 'rows', 'store', 'times_sampled', 'pos')
+  """`pos` = index into the table's dense arrays (priority, times sampled, key, rows)."""
+  __slots__ = ('key', 'priority', 'rows', 'store', 'pos')
 
   def __init__(self, key, priority, rows, store):
     self.key, self.priority, self.rows, self.store = key, float(priority), rows, store
-    self.times_sampled = 0
     self.pos = -1
 
 
@@ -156,6 +159,19 @@ class _SumTree(object):
   def get(self, pos):
     return float(self._t[pos + self._cap]) if pos < self._cap else 0.0
 
+  def find_many(self, u):
+    """`find` for a vector of `u`: one numpy step per tree level."""
+    i = np.ones(u.shape, np.int64)
+    u = u.astype(np.float64).copy()
+    cap = self._cap
+    while cap > 1:
+      left = self._t[2 * i]
+      right = u >= left
+      u -= np.where(right, left, 0.0)
+      i = 2 * i + right
+      cap >>= 1
+    return i - self._cap
+
   def find(self, u):
     """Position whose cumulative-weight interval contains `u` in [0, total)."""
     i = 1
@@ -185,6 +201,13 @@ class Table(object):
     self._by_key = collections.OrderedDict()      # insertion order = FIFO order
     self._dense = []                              # positions for O(1) uniform draws
     self._prio = np.zeros(64, np.float64)         # priorities aligned with _dense
+    self._times = np.zeros(64, np.int64)          # times sampled, aligned with _dense
+    self._keys = np.zeros(64, np.int64)           # item keys, aligned with _dense
+    # [position, T] step rows while every item has the same length and row pool (the vectorised
+    # batch path of `sample_rows`); None once items of another length / pool were inserted
+    self._rows2d = None
+    self._rows_ok = True
+    self._pool = None
     self._num_unique_samples = 0
     self._server = None
     self._tree = _SumTree() if isinstance(sampler, Prioritized) else None   # p^exponent per position
@@ -222,22 +245,45 @@ class Table(object):
                      else 0.0)
 
   def _put(self, item):
-    item.pos = len(self._dense)
+    pos = item.pos = len(self._dense)
     self._dense.append(item)
-    if item.pos >= self._prio.shape[0]:
+    if pos >= self._prio.shape[0]:
       self._prio = np.concatenate([self._prio, np.zeros_like(self._prio)])
-    self._set_weight(item.pos, item.priority)
+      self._times = np.concatenate([self._times, np.zeros_like(self._times)])
+      self._keys = np.concatenate([self._keys, np.zeros_like(self._keys)])
+      if self._rows2d is not None:
+        self._rows2d = np.concatenate([self._rows2d, np.zeros_like(self._rows2d)])
+    self._set_weight(pos, item.priority)
+    self._times[pos] = 0
+    self._keys[pos] = item.key
     self._by_key[item.key] = item
+    # the [position, T] row matrix of the vectorised batch path
+    if self._rows_ok:
+      if self._rows2d is None and self._pool is None:
+        self._pool = item.store
+        self._rows2d = np.zeros((self._prio.shape[0], item.rows.shape[0]), np.int64)
+      if item.store is not self._pool or item.rows.shape[0] != self._rows2d.shape[1]:
+        self._rows_ok, self._rows2d = False, None       # mixed lengths / pools: generic path only
+      else:
+        self._rows2d[pos] = item.rows
 
   def _drop(self, item):
     last = self._dense.pop()
-    self._set_weight(len(self._dense), 0.0)       # the vacated last position
+    n = len(self._dense)
+    self._set_weight(n, 0.0)                      # the vacated last position
     if last is not item:
-      self._dense[item.pos] = last
-      last.pos = item.pos
-      self._set_weight(last.pos, last.priority)
+      pos = item.pos
+      self._dense[pos] = last
+      last.pos = pos
+      self._set_weight(pos, last.priority)
+      self._times[pos] = self._times[n]
+      self._keys[pos] = self._keys[n]
+      if self._rows2d is not None:
+        self._rows2d[pos] = self._rows2d[n]
     del self._by_key[item.key]
     item.store.release(item.rows)
+    if not self._dense and not self._rows_ok:     # an emptied table may take the fast path again
+      self._rows_ok, self._rows2d, self._pool = True, None, None
 
   def _victim(self):
     r = self._remover
@@ -318,15 +364,50 @@ class Table(object):
             'Table {!r} holds {} item(s); its rate limiter needs {} to sample.'.format(
                 self.name, self.current_size, max(1, self._rate_limiter.min_size_to_sample)))
       item, prob = self._pick()
-      if item.times_sampled == 0:
+      if self._times[item.pos] == 0:
         self._num_unique_samples += 1
-      item.times_sampled += 1
-      info = SampleInfo(item.key, prob, self.current_size, item.priority, item.times_sampled)
+      self._times[item.pos] += 1
+      times = int(self._times[item.pos])
+      info = SampleInfo(item.key, prob, self.current_size, item.priority, times)
       item.store.retain(item.rows)                 # pinned for the reader
       out.append((item, info))
-      if self._max_times_sampled > 0 and item.times_sampled >= self._max_times_sampled:
+      if self._max_times_sampled > 0 and times >= self._max_times_sampled:
         self._drop(item)
     return out
+
+  def sample_rows(self, num_samples):
+    """Vectorised batch draw: `(pool, rows[num_samples, T], SampleInfo of arrays)`, or None when the
+    table needs the item-by-item path (`max_times_sampled`, items of different lengths or row
+    pools, a sampler other than Uniform / Prioritized).  No python work per sample: positions are
+    drawn at once (sum-tree descent over the whole vector for Prioritized) and the step rows come
+    from the dense `[position, T]` matrix, ready for ONE gather launch."""
+    n = len(self._dense)
+    if (self._max_times_sampled > 0 or self._rows2d is None or
+        not isinstance(self._sampler, (Uniform, Prioritized))):
+      return None
+    if not self.can_sample(1):
+      raise RateLimited(
+          'Table {!r} holds {} item(s); its rate limiter needs {} to sample.'.format(
+              self.name, n, max(1, self._rate_limiter.min_size_to_sample)))
+    rng = self._server.rng
+    total = self._tree.total if self._tree is not None else 0.0
+    if self._tree is not None and total > 0:
+      pos = self._tree.find_many(rng.random(num_samples) * total)
+      w = self._tree._t[self._tree._cap + np.minimum(pos, n - 1)]
+      bad = (pos >= n) | ~(w > 0)                  # rounding at an interval edge
+      if bad.any():
+        pos = np.where(bad, int(np.argmax(self._prio[:n] > 0)), pos)
+        w = self._tree._t[self._tree._cap + pos]
+      prob = w / total
+    else:
+      pos = rng.integers(n, size=num_samples)
+      prob = np.full(num_samples, 1.0 / n)
+    fresh = np.unique(pos[self._times[pos] == 0])
+    self._num_unique_samples += int(fresh.size)
+    np.add.at(self._times, pos, 1)
+    info = SampleInfo(self._keys[pos].copy(), prob, np.full(num_samples, n, np.int64),
+                      self._prio[pos].copy(), self._times[pos].copy())
+    return self._pool, self._rows2d[pos], info
 
   @staticmethod
   def release_samples(samples):

@@ -701,3 +701,62 @@ def test_prioritized_sum_tree_tracks_inserts_evictions_and_updates():
   sigma = np.sqrt(n_draws * p * (1 - p)) + 1e-9
   assert np.all(np.abs(counts - n_draws * p) <= 5 * sigma + 1)
   assert counts[p == 0].sum() == 0
+
+
+@pytest.mark.parametrize('sampler', [reverb.selectors.Uniform(), reverb.selectors.Prioritized(0.8)])
+def test_vectorised_batches_follow_the_sampling_law(sampler):
+  """`Table.sample_rows` (whole batches drawn as vectors) against the selector's law, its
+  SampleInfo arrays and its counters; the table leaves the fast path for good when an item of
+  another length arrives and takes it again after a reset."""
+  table = reverb.Table('v', sampler=sampler, remover=reverb.selectors.Fifo(), max_size=64,
+                       rate_limiter=reverb.rate_limiters.MinSize(1))
+  srv = _server([table], capacity=512)
+  client = srv.localhost_client()
+  rng = np.random.default_rng(5)
+  prios = rng.integers(0, 5, size=200).astype(float) + (0 if isinstance(
+      sampler, reverb.selectors.Prioritized) else 1)
+  with client.trajectory_writer(3) as w:
+    for i in range(200):
+      w.append(np.int64(i))
+      if i:
+        w.create_item('v', trajectory=w.history[-2:], priority=prios[i])
+  n = table.current_size
+  assert n == 64
+  if isinstance(sampler, reverb.selectors.Prioritized):
+    wgt = np.array([it.priority ** 0.8 if it.priority > 0 else 0.0 for it in table._dense])
+  else:
+    wgt = np.ones(n)
+  p = wgt / wgt.sum()
+  pos_of = {it.key: i for i, it in enumerate(table._dense)}
+  counts, draws = np.zeros(n), 0
+  for _ in range(100):
+    pool, rows, info = table.sample_rows(256)
+    assert rows.shape == (256, 2) and info.key.shape == (256,) and info.table_size[0] == n
+    pos = np.array([pos_of[int(k)] for k in info.key])
+    np.testing.assert_array_equal(rows, np.stack([table._dense[i].rows for i in pos]))
+    np.testing.assert_allclose(info.probability, p[pos], rtol=1e-9)
+    np.testing.assert_array_equal(info.priority, [table._dense[i].priority for i in pos])
+    data = pool.read(rows)[0]
+    np.testing.assert_array_equal(data[:, 0] + 1, data[:, 1])       # consecutive steps
+    counts += np.bincount(pos, minlength=n)
+    draws += 256
+  sigma = np.sqrt(draws * p * (1 - p))
+  assert np.all(np.abs(counts - draws * p) <= 5 * sigma + 1) and counts[p == 0].sum() == 0
+  np.testing.assert_array_equal(table._times[:n], counts)
+  assert table.info.num_unique_samples == int((counts > 0).sum())
+  assert srv.live_rows() == 65 + 0          # 64 overlapping windows of 2 -> 65 steps; no reader pins
+  with client.trajectory_writer(4) as w:   # an item of another length: generic path from now on
+    for i in range(3):
+      w.append(np.int64(1000 + i))
+    w.create_item('v', trajectory=w.history[-3:], priority=1)
+  assert table.sample_rows(4) is None
+  replay = _scalar_replay(table, srv, sequence_length=None)
+  it = iter(replay.as_dataset(sample_batch_size=1))    # falls back to item-by-item batches
+  lengths = {next(it)[0].shape[1] for _ in range(300)}
+  assert lengths == {2, 3} or lengths == {2}
+  table.reset()
+  with client.trajectory_writer(3) as w:
+    for i in range(5):
+      w.append(np.int64(i))
+      w.create_item('v', trajectory=w.history[-1:], priority=1)
+  assert table.sample_rows(4)[1].shape == (4, 1)

@@ -18,7 +18,7 @@ from hypothesis import given, settings, strategies as st  # noqa: E402
 from agents_b200.replay_buffers import reverb_local as reverb  # noqa: E402
 import py_env_mocks  # noqa: E402
 
-OPS = st.lists(st.tuples(st.sampled_from(['append', 'item', 'end', 'sample', 'reset', 'flush']),
+OPS = st.lists(st.tuples(st.sampled_from(['append', 'item', 'end', 'sample', 'batch', 'reset', 'flush']),
                          st.integers(min_value=1, max_value=4)), min_size=1, max_size=60)
 
 
@@ -48,6 +48,13 @@ def test_row_pool_matches_model(ops, max_size, keep, times, stage, sampler):
       got = it.store.read(it.rows)[0]
       np.testing.assert_array_equal(got, items[it.key])
     assert set(items) == {it.key for it in table._dense}
+    # dense arrays follow the swap-removes: keys, and the [position, T] row matrix while it exists
+    for i, it in enumerate(table._dense):
+      assert it.pos == i and table._keys[i] == it.key
+      if table._rows2d is not None:
+        np.testing.assert_array_equal(table._rows2d[i], it.rows)
+    if table._rows2d is None and table._dense:
+      assert len({it.rows.shape[0] for it in table._dense}) > 1 or not table._rows_ok
     if table._tree is not None:          # sum tree == p^0.5 at the live positions, 0 beyond them
       n = table.current_size
       for i, it in enumerate(table._dense):
@@ -98,6 +105,19 @@ def test_row_pool_matches_model(ops, max_size, keep, times, stage, sampler):
       for key in list(items):
         if key not in alive:                                   # reached max_times_sampled
           del items[key]
+    elif op == 'batch' and table.can_sample(1):
+      drawn = table.sample_rows(3)
+      if drawn is not None:                # fixed-length items, no max_times_sampled
+        pool, rows, info = drawn
+        by_key = {it.key: it for it in table._dense}
+        got = pool.read(rows)[0]
+        for b in range(3):
+          np.testing.assert_array_equal(rows[b], by_key[int(info.key[b])].rows)
+          np.testing.assert_array_equal(got[b], items[int(info.key[b])])
+          assert info.times_sampled[b] >= 1 and 0 < info.probability[b] <= 1
+      else:
+        assert (times > 0 or isinstance(sampler, reverb.selectors.Fifo) or
+                len({it.rows.shape[0] for it in table._dense}) > 1 or not table._rows_ok)
     elif op == 'reset':
       table.reset()
       items.clear()
