@@ -32,7 +32,8 @@ class EpsilonGreedyPolicy(_Selecting):
   def _get_epsilon(self):
     if not callable(self._epsilon):
       return self._epsilon
-    if not self._warned_capture and torch.cuda.is_current_stream_capturing():
+    if (not self._warned_capture and torch.cuda.is_available() and
+        torch.cuda.is_current_stream_capturing()):
       # the launch takes epsilon BY VALUE: inside common.function (a CUDA graph) the value seen
       # at capture time is replayed, unlike a tf.Variable read inside a tf.function
       warnings.warn('EpsilonGreedyPolicy: a callable epsilon is evaluated once when the collect '
