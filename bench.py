@@ -22,6 +22,8 @@ target update every 2500 steps.  One "step" = get_next(256, 2) + DqnAgent.train(
   ppo_update / sac_step / cartpole_iter / gather_sweep   BASELINE configs 3 / 4 / 1 / 5
                (profiles/configs.py); under torchrun they are sharded over the ranks.
   dp_parity    (N > 1) N replicas on shards vs one replica on the whole batch.
+The main line is complete before the extra configs and the CPU arm start; they only add keys, and
+a watchdog (`--extras-timeout`, 600 s) prints the line without them should one of them hang.
 
 `--impl reference` times that CPU restatement alone (the reference arm of the contract).
 N>1 (torchrun): one process per GPU, each with its own 1M-slot ring shard and a local batch of
